@@ -1,0 +1,155 @@
+/* libleann_b200 — C ABI of the B200-native selective-recompute search path.
+ *
+ * Drop-in boundary for LEANN's HNSW backend search path.  Every entry point names the
+ * reference interface it replaces (paths under /root/reference/packages/):
+ *
+ *   lb2_open            faiss.read_index(file, IO_FLAG_MMAP, HNSWIndexConfig)
+ *                         leann-backend-hnsw/leann_backend_hnsw/hnsw_backend.py:141-151
+ *                         -> third_party/faiss/faiss/impl/index_read.cpp:1402-1490, 523-813
+ *   lb2_search          IndexHNSW::search(n, x, k, D, I, SearchParametersHNSW*)
+ *                         hnsw_backend.py:241-248 -> faiss/IndexHNSW.cpp:419-439
+ *   lb2_search_params   faiss::SearchParametersHNSW            faiss/impl/HNSW.h:54-73
+ *   lb2_set_passages /  the embedding server's start-up inputs (passages file + model):
+ *   lb2_set_encoder       leann-core/src/leann/embedding_server_manager.py:151-174,
+ *                         hnsw_embedding_server.py:36-96 ; they feed the recompute stage that
+ *                         replaces ZmqDistanceComputer::distances_batch
+ *                         (faiss/impl/HNSW_zmq.cpp:579-654 -> hnsw_embedding_server.py:147-211)
+ *   lb2_set_vectors     the IndexFlat storage of a non-pruned index (recompute_embeddings=False)
+ *   lb2_encode_ids      embedding-server "ids -> embeddings" branch   hnsw_embedding_server.py:213-284
+ *   lb2_encode_tokens   embedding-server "texts -> embeddings" branch hnsw_embedding_server.py:134-145
+ *                         (compute_query_embedding, leann-core/src/leann/searcher_base.py:86-128)
+ *   lb2_close           Index destructor / EmbeddingServerManager.stop_server
+ *   lb2_last_error      FaissException text surfaced as Python RuntimeError by SWIG
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; functions return 0 on success
+ * and a negative code on failure (message via lb2_last_error(), thread-local); nothing throws
+ * across the boundary.  Pointers are HOST pointers unless the name says device.  The library
+ * needs a CUDA device of compute capability 10.x; there is no CPU path.
+ */
+#ifndef LEANN_B200_H
+#define LEANN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB2_OK 0
+#define LB2_ERR_ARG (-1)
+#define LB2_ERR_IO (-2)
+#define LB2_ERR_CUDA (-3)
+#define LB2_ERR_STATE (-4)
+#define LB2_ERR_UNSUPPORTED (-5)
+
+typedef struct lb2_index lb2_index; /* opaque */
+
+/* faiss::SearchParametersHNSW (faiss/impl/HNSW.h:54-73) + the backend's recompute switch */
+typedef struct {
+    int32_t efSearch;                /* "complexity" of LeannSearcher.search; default 64          */
+    int32_t beam_size;               /* "beam_width"; candidates expanded per hop; default 1       */
+    int32_t batch_size;              /* expand until >= batch_size neighbours gathered; 0 = off    */
+    int32_t check_relative_distance; /* stop rule of HNSW_search.cpp:583-592; default 1            */
+    float pq_pruning_ratio;          /* "prune_ratio"; must be 0 (PQ pruning: SURVEY 8f row 3)     */
+    int32_t local_prune;             /* must be 0                                                  */
+    float send_neigh_times_ratio;    /* must be 0                                                  */
+    int32_t recompute;               /* 1: recompute embeddings on the GPU (default); 0: stored    */
+} lb2_search_params;
+
+typedef struct {
+    int64_t ndis;            /* sum over queries of HNSWStats.ndis  (faiss/impl/HNSW.h:353-361)   */
+    int64_t nhops;           /* sum over queries of HNSWStats.nhops                                 */
+    int64_t n_recomputed;    /* passages encoded (after cross-query de-duplication per hop)        */
+    int64_t n_requested;     /* (query, node) distance requests = ndis + entry points              */
+    int64_t n_tokens;        /* tokens pushed through the encoder                                   */
+    int64_t n_steps;         /* traversal kernel launches                                           */
+    int64_t n_kernel_launches; /* all kernels launched by this call                                 */
+    double gpu_ms;           /* device time of the call (CUDA events on the launching stream)      */
+    double encoder_ms;       /* of which recompute stage                                           */
+    double gemm_ms;          /* of which tcgen05 GEMMs (only when LB2_PROFILE_GEMM=1)               */
+    double gemm_flops;       /* algorithmic flops of those GEMMs                                    */
+} lb2_search_stats;
+
+typedef struct {
+    int64_t ntotal;
+    int32_t d;
+    int32_t metric_type; /* faiss MetricType: 0 inner product, 1 L2 */
+    int32_t entry_point;
+    int32_t max_level;
+    int64_t n_edges;
+    int32_t max_degree_level0;
+    int32_t max_degree_upper;
+    int32_t has_vectors;
+    int32_t has_passages;
+    int32_t has_encoder;
+    int32_t device;
+} lb2_index_info;
+
+/* BERT-family encoder description (architecture constants of the model card) */
+typedef struct {
+    int32_t vocab_size, hidden, layers, heads, ffn, max_pos, type_vocab;
+    float ln_eps;
+    int32_t pooling;   /* 0 masked mean, 1 CLS */
+    int32_t normalize; /* 1: L2-normalise (Normalize module) */
+} lb2_encoder_config;
+
+const char* lb2_last_error(void);
+int lb2_version(void);
+
+/* Reads the reference's compact-CSR `.index` file and uploads the graph to `device`. */
+lb2_index* lb2_open(const char* index_path, int device);
+void lb2_close(lb2_index* idx);
+int lb2_info(const lb2_index* idx, lb2_index_info* out);
+
+/* Stored-vector mode (non-pruned index): x is [ntotal, d] fp32. */
+int lb2_set_vectors(lb2_index* idx, const float* x);
+
+/* Pre-tokenised passage store: passage i = tokens[offsets[i] .. offsets[i+1]) (WordPiece ids incl.
+ * [CLS]/[SEP], as the reference's tokenizer would produce them), ntotal+1 offsets. */
+int lb2_set_passages(lb2_index* idx, const uint16_t* tokens, const uint64_t* offsets);
+
+/* Weights: one fp32 blob, tensors in this order (nn.Linear weights are [out, in]):
+ *   word_emb[V,H] pos_emb[P,H] type_emb[T,H] emb_ln_g[H] emb_ln_b[H]
+ *   per layer: w_qkv[3H,H] (q,k,v rows stacked) b_qkv[3H] w_o[H,H] b_o[H] ln1_g[H] ln1_b[H]
+ *              w_1[F,H] b_1[F] w_2[H,F] b_2[H] ln2_g[H] ln2_b[H]
+ * Stored on the device as fp16 matrices / fp32 vectors (the reference loads fp16 too). */
+size_t lb2_encoder_weight_count(const lb2_encoder_config* cfg);
+int lb2_set_encoder(lb2_index* idx, const lb2_encoder_config* cfg, const float* weights, size_t n_floats);
+
+void lb2_default_params(lb2_search_params* p);
+
+/* q: [nq, d] fp32 (already normalised for cosine); D: [nq, k]; I: [nq, k].  Labels are the
+ * internal int64 ids; distances are +inner product (descending) for IP metrics, squared L2
+ * (ascending) otherwise; unfilled slots are (-1, -/+FLT_MAX) like faiss. */
+int lb2_search(lb2_index* idx, int64_t nq, const float* q, int64_t k, float* D, int64_t* I,
+               const lb2_search_params* params, lb2_search_stats* stats);
+/* Same, all three buffers already resident in device memory. */
+int lb2_search_device(lb2_index* idx, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
+                      const lb2_search_params* params, lb2_search_stats* stats);
+/* Per-query HNSWStats of the last search call ([nq] each, host). */
+int lb2_last_query_stats(lb2_index* idx, int64_t nq, int64_t* ndis, int64_t* nhops);
+
+/* Recompute stage alone. */
+int lb2_encode_ids(lb2_index* idx, int64_t n, const int64_t* ids, float* out /* [n, d] */);
+int lb2_encode_tokens(lb2_index* idx, int64_t n, const uint16_t* tokens, const uint64_t* offsets /* n+1 */,
+                      float* out /* [n, d] */);
+/* passages [first, first+n) of the attached store -> DEVICE buffer d_out [n, d] (index building) */
+int lb2_encode_range_device(lb2_index* idx, int64_t first, int64_t n, float* d_out);
+
+/* Tunables (0 keeps the current value): traversal slots in flight, passages per encoder pass. */
+int lb2_configure(lb2_index* idx, int32_t slots, int32_t passages_per_pass);
+
+/* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
+int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
+                      int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);
+int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden,
+                           float eps);
+/* qkv: packed [sum(len), 3*hidden] fp16 on the device; h_seq_len: HOST int32[n_seq] */
+int lb2_test_attention_f16(const void* dqkv, const int32_t* h_seq_len, int n_seq, int hidden, int heads,
+                           int max_len, void* dctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEANN_B200_H */

@@ -1,0 +1,190 @@
+"""Tooling (not the hot path): builds an HNSW-shaped graph in the reference's CSR format
+from a matrix of embeddings, with torch ops (CUDA when available, CPU for small tests).
+
+SURVEY.md §8(f) row 1 — the reference builds with faiss' incremental insertion
+(faiss/IndexHNSW.cpp:59-280, impl/HNSW.cpp:426-894), hours at 10 M points on CPU.  The search
+path only needs *a* navigable HNSW-format graph that both the reference CPU search and the CUDA
+search traverse identically, so this builder takes the batch route:
+  * levels drawn like HNSW::random_level (impl/HNSW.cpp:182-193, level_mult = 1/ln M);
+  * per level: candidates = exact k-nearest members (blocked GEMM + top-k) plus the nearest members
+    of the next two levels up (sparser samples -> longer links, standing in for HNSW's early
+    insertions), pruned with the HNSW neighbour-selection heuristic (keep a candidate only if it is closer to
+    the node than to every already kept neighbour — shrink_neighbor_list, impl/HNSW.cpp:426-480),
+    then reverse edges added and each list capped to M (2M on level 0) nearest;
+  * entry point = first node of the top level.
+Output is a leann_b200.csr.CSRGraph, written with csr.write_compact_index().
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .csr import METRIC_INNER_PRODUCT, METRIC_L2, CSRGraph, csr_from_padded
+
+
+def draw_levels(n: int, M: int, seed: int = 12345) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    mult = 1.0 / np.log(M)
+    lv = np.floor(-np.log(1.0 - rng.random(n)) * mult).astype(np.int32) + 1
+    return np.minimum(lv, 8)
+
+
+@torch.no_grad()
+def _knn(xq: torch.Tensor, xb: torch.Tensor, k: int, metric_ip: bool, self_pos: torch.Tensor | None = None,
+         block: int = 4096) -> tuple[torch.Tensor, torch.Tensor]:
+    """Exact kNN of every row of xq among the rows of xb.  self_pos[i] = row of xb that IS query i
+    (excluded) or -1.  Returns (idx [n,k] into xb, 'distance' [n,k]) with distance = -ip or squared
+    L2 (smaller = closer), ascending."""
+    n = xq.shape[0]
+    k = max(1, min(k, xb.shape[0] - 1))
+    xqs, xbs = (xq.half(), xb.half()) if xq.is_cuda else (xq, xb)
+    sqq, sqb = (xq * xq).sum(1), (xb * xb).sum(1)
+    idx = torch.empty((n, k), dtype=torch.int64, device=xq.device)
+    dist = torch.empty((n, k), dtype=torch.float32, device=xq.device)
+    for b0 in range(0, n, block):
+        b1 = min(n, b0 + block)
+        ip = (xqs[b0:b1] @ xbs.T).float()
+        d = -ip if metric_ip else (sqq[b0:b1, None] + sqb[None, :] - 2 * ip)
+        if self_pos is not None:
+            sp = self_pos[b0:b1]
+            m = sp >= 0
+            d[torch.nonzero(m)[:, 0], sp[m]] = float("inf")
+        dv, di = torch.topk(d, k, dim=1, largest=False)
+        idx[b0:b1] = di
+        dist[b0:b1] = dv
+    return idx, dist
+
+
+@torch.no_grad()
+def _heuristic_prune(x: torch.Tensor, cand: torch.Tensor, cdist: torch.Tensor, keep: int, metric_ip: bool,
+                     fill: bool, block: int = 8192) -> torch.Tensor:
+    """HNSW neighbour selection over candidates sorted by distance (padding = -1 / +inf at the end);
+    returns idx [n, keep] padded with -1.  fill=True tops the list up with the nearest pruned candidates."""
+    n, K = cand.shape
+    out = torch.full((n, keep), -1, dtype=torch.int64, device=x.device)
+    xs = x.half() if x.is_cuda else x
+    sq = (x * x).sum(1)
+    for b0 in range(0, n, block):
+        b1 = min(n, b0 + block)
+        c = cand[b0:b1]
+        valid = c >= 0
+        c = c.clamp(min=0)
+        cv = xs[c]  # [b, K, d]
+        ip = torch.bmm(cv, cv.transpose(1, 2)).float()
+        pd = -ip if metric_ip else (sq[c][:, :, None] + sq[c][:, None, :] - 2 * ip)  # dist(c_i, c_j)
+        dn = cdist[b0:b1]  # dist(node, c_j)
+        kept = torch.zeros((b1 - b0, K), dtype=torch.bool, device=x.device)
+        nk = torch.zeros(b1 - b0, dtype=torch.int64, device=x.device)
+        for j in range(K):
+            # c_j is dominated if some kept c_i is closer to c_j than the node is
+            dom = ((pd[:, :, j] < dn[:, j:j + 1]) & kept).any(1)
+            ok = (~dom) & (nk < keep) & valid[:, j]
+            kept[:, j] = ok
+            nk += ok.long()
+        # kept first (in distance order), then — if fill — the nearest pruned candidates
+        rank = torch.arange(K, device=x.device)[None, :].expand_as(kept)
+        prio = torch.where(kept, rank, rank + K)
+        prio = torch.where(valid & (kept | fill), prio, torch.full_like(prio, 4 * K))
+        order = torch.argsort(prio, dim=1)[:, :keep]
+        sel = torch.gather(c, 1, order)
+        selp = torch.gather(prio, 1, order)
+        sel = torch.where(selp < 4 * K, sel, torch.full_like(sel, -1))
+        out[b0:b1, : sel.shape[1]] = sel
+    return out
+
+
+@torch.no_grad()
+def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip: bool):
+    """Symmetrise: union of forward and reverse edges, keep the `cap` nearest per node, sorted by
+    distance.  Returns (idx [n, cap] padded -1, dist [n, cap] padded +inf)."""
+    n, K = nbr.shape
+    dev = x.device
+    src = torch.arange(n, device=dev)[:, None].expand(n, K).reshape(-1)
+    dst = nbr.reshape(-1)
+    m = dst >= 0
+    src, dst = src[m], dst[m]
+    a = torch.cat([src, dst])
+    b = torch.cat([dst, src])
+    key = torch.unique(a * n + b)
+    a, b = key // n, key % n
+    xs = x.half() if x.is_cuda else x
+    if metric_ip:
+        d = -(xs[a].float() * xs[b].float()).sum(1)
+    else:
+        d = ((xs[a].float() - xs[b].float()) ** 2).sum(1)
+    # sort by (a, d): stable two-pass
+    o = torch.argsort(d, stable=True)
+    a, b, d = a[o], b[o], d[o]
+    o = torch.argsort(a, stable=True)
+    a, b, d = a[o], b[o], d[o]
+    counts = torch.bincount(a, minlength=n)
+    starts = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(a.numel(), device=dev) - starts[a]
+    keepm = rank < cap
+    out = torch.full((n, cap), -1, dtype=torch.int64, device=dev)
+    out[a[keepm], rank[keepm]] = b[keepm]
+    outd = torch.full((n, cap), float("inf"), dtype=torch.float32, device=dev)
+    outd[a[keepm], rank[keepm]] = d[keepm].float()
+    return out, outd
+
+
+@torch.no_grad()
+def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
+                     knn_factor: float = 1.5, n_scales: int = 2, verbose: bool = False) -> CSRGraph:
+    metric_ip = metric.lower() in ("mips", "cosine", "ip")
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    x = emb if isinstance(emb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(emb, np.float32))
+    x = x.to(dev, torch.float32)
+    n, d = x.shape
+    levels = draw_levels(n, M, seed)
+    max_level = int(levels.max()) - 1
+    level0 = None
+    upper = {}
+    for l in range(max_level, -1, -1):
+        members = np.nonzero(levels > l)[0]
+        cap = 2 * M if l == 0 else M
+        if len(members) <= 1:
+            nb = np.full((len(members), cap), -1, np.int32)
+        else:
+            mt = torch.from_numpy(members).to(dev)
+            xm = x[mt]
+            nm = len(members)
+            # multi-scale candidates: nearest members, plus nearest among the (sparser) members of
+            # the next levels up.  The sparse samples play the role of HNSW's early insertions and
+            # supply the long links a pure kNN graph lacks.
+            ci, cd = _knn(xm, xm, int(cap * knn_factor), metric_ip, torch.arange(nm, device=dev))
+            cis, cds = [ci], [cd]
+            for s_up in range(1, n_scales + 1):
+                sub = np.nonzero(levels[members] > l + s_up)[0]
+                if len(sub) < 2:
+                    break
+                st = torch.from_numpy(sub).to(dev)
+                pos = torch.full((nm,), -1, dtype=torch.int64, device=dev)
+                pos[st] = torch.arange(len(sub), device=dev)
+                di, dv = _knn(xm, xm[st], max(2, cap // 2), metric_ip, pos)
+                cis.append(st[di])
+                cds.append(dv)
+            ci, cd = torch.cat(cis, 1), torch.cat(cds, 1)
+            o = torch.argsort(cd, dim=1, stable=True)
+            ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+            o = torch.argsort(ci, dim=1, stable=True)  # group equal ids (distance order kept inside a group)
+            ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+            dup = torch.zeros_like(ci, dtype=torch.bool)
+            dup[:, 1:] = ci[:, 1:] == ci[:, :-1]
+            ci = torch.where(dup, torch.full_like(ci, -1), ci)
+            cd = torch.where(dup, torch.full_like(cd, float("inf")), cd)
+            o = torch.argsort(cd, dim=1, stable=True)
+            ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+            fwd = _heuristic_prune(xm, ci, cd, cap, metric_ip, fill=False)
+            ui, ud = _add_reverse_and_cap(xm, fwd, 2 * cap, metric_ip)
+            both = _heuristic_prune(xm, ui, ud, cap, metric_ip, fill=True)
+            gl = torch.where(both >= 0, mt[both.clamp(min=0)], torch.full_like(both, -1))
+            nb = gl.cpu().numpy().astype(np.int32)
+        if l == 0:
+            level0 = nb
+        else:
+            upper[l] = (members.astype(np.int64), nb)
+        if verbose:
+            print(f"  level {l}: {len(members)} nodes, mean degree {(nb >= 0).sum(1).mean():.1f}")
+    entry = int(np.nonzero(levels == levels.max())[0][0])
+    return csr_from_padded(d, METRIC_INNER_PRODUCT if metric_ip else METRIC_L2, levels, level0, upper, entry, M=M)

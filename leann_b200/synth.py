@@ -1,0 +1,164 @@
+"""Synthetic inputs for tests and the benchmark (there is no network for real weights / corpora).
+
+* encoder presets with the architecture constants of the two models BASELINE.json names
+  (all-MiniLM-L6-v2, bge-base-en-v1.5; public model cards);
+* seeded synthetic weights, packed in the blob order lb2_set_encoder() documents;
+* topic-structured token corpora: K = sqrt(N) topics, each a peaked
+  distribution over a private sub-vocabulary, mixed 80/20 with a global Zipf background,
+  so that mean-pooled embeddings have a non-degenerate neighbourhood structure.
+
+Everything here is deterministic in (seed, sizes) and uses numpy only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .capi import EncoderConfig
+
+CLS_ID, SEP_ID = 101, 102
+FIRST_WORD_ID = 1000
+
+
+@dataclass(frozen=True)
+class ModelPreset:
+    name: str
+    vocab_size: int
+    hidden: int
+    layers: int
+    heads: int
+    ffn: int
+    max_pos: int  # max_seq_length the sentence-transformers wrapper truncates to
+    type_vocab: int
+    ln_eps: float
+    pooling: int  # 0 mean, 1 cls
+    normalize: int
+
+    def config(self) -> EncoderConfig:
+        return EncoderConfig(self.vocab_size, self.hidden, self.layers, self.heads, self.ffn, self.max_pos,
+                             self.type_vocab, self.ln_eps, self.pooling, self.normalize)
+
+    def flops_per_chunk(self, L: int) -> float:
+        """F(L) of SURVEY.md §8d: layers * L * (2*(4h^2 + 2hf) + 4*L*h)."""
+        h, f = self.hidden, self.ffn
+        return self.layers * L * (2.0 * (4 * h * h + 2 * h * f) + 4.0 * L * h)
+
+
+MINILM_L6 = ModelPreset("sentence-transformers/all-MiniLM-L6-v2", 30522, 384, 6, 12, 1536, 256, 2, 1e-12, 0, 1)
+BGE_BASE = ModelPreset("BAAI/bge-base-en-v1.5", 30522, 768, 12, 12, 3072, 512, 2, 1e-12, 1, 1)
+TINY = ModelPreset("synthetic/tiny-bert", 2048, 384, 2, 12, 768, 64, 2, 1e-12, 0, 1)  # fast CPU-oracle tests
+PRESETS = {p.name: p for p in (MINILM_L6, BGE_BASE, TINY)}
+
+
+def weight_layout(p: ModelPreset) -> list[tuple[str, tuple[int, ...]]]:
+    """(name, shape) in blob order — the order documented in include/leann_b200.h."""
+    H, F = p.hidden, p.ffn
+    out = [("word_emb", (p.vocab_size, H)), ("pos_emb", (p.max_pos, H)), ("type_emb", (p.type_vocab, H)),
+           ("emb_ln_g", (H,)), ("emb_ln_b", (H,))]
+    for l in range(p.layers):
+        out += [(f"l{l}.w_qkv", (3 * H, H)), (f"l{l}.b_qkv", (3 * H,)), (f"l{l}.w_o", (H, H)), (f"l{l}.b_o", (H,)),
+                (f"l{l}.ln1_g", (H,)), (f"l{l}.ln1_b", (H,)), (f"l{l}.w_1", (F, H)), (f"l{l}.b_1", (F,)),
+                (f"l{l}.w_2", (H, F)), (f"l{l}.b_2", (H,)), (f"l{l}.ln2_g", (H,)), (f"l{l}.ln2_b", (H,))]
+    return out
+
+
+def synthetic_weights(p: ModelPreset, seed: int = 0) -> dict[str, np.ndarray]:
+    """Seeded fp32 tensors.  Matrices are rounded through fp16 so the fp32 oracle and the fp16
+    device copy hold the same values (the reference loads fp16 weights, embedding_compute.py:157-158)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, shape in weight_layout(p):
+        base = name.split(".")[-1]
+        if base == "word_emb":
+            a = rng.normal(0, 0.10, shape)
+        elif base in ("pos_emb", "type_emb"):
+            a = rng.normal(0, 0.02, shape)
+        elif base.endswith("_g"):
+            a = 1.0 + rng.normal(0, 0.05, shape)
+        elif base.startswith("b_") or base.endswith("_b"):
+            a = rng.normal(0, 0.02, shape)
+        else:  # linear weights
+            a = rng.normal(0, 0.04, shape)
+        a = a.astype(np.float32)
+        if len(shape) == 2:
+            a = a.astype(np.float16).astype(np.float32)
+        w[name] = a
+    return w
+
+
+def pack_weights(p: ModelPreset, w: dict[str, np.ndarray]) -> np.ndarray:
+    return np.concatenate([np.ascontiguousarray(w[name], np.float32).reshape(-1) for name, _ in weight_layout(p)])
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Corpus:
+    tokens: np.ndarray   # uint16 [total]
+    offsets: np.ndarray  # uint64 [n + 1]
+    topics: np.ndarray   # int32 [n]
+
+    @property
+    def n(self) -> int:
+        return self.offsets.size - 1
+
+    def passage(self, i: int) -> np.ndarray:
+        return self.tokens[int(self.offsets[i]): int(self.offsets[i + 1])]
+
+
+class TopicModel:
+    """K topics over a vocabulary; shared by the corpus and the query generator."""
+
+    def __init__(self, vocab_size: int, n_topics: int, seed: int = 1234, sub_vocab: int = 2048, alpha: float = 0.05):
+        rng = np.random.default_rng(seed)
+        self.vocab_size = vocab_size
+        self.n_topics = n_topics
+        nwords = vocab_size - FIRST_WORD_ID
+        sub_vocab = min(sub_vocab, nwords)
+        self.sub_vocab = sub_vocab
+        # private sub-vocabulary and peaked weights per topic
+        self.topic_words = np.stack([rng.choice(nwords, sub_vocab, replace=False) for _ in range(n_topics)]).astype(np.int32) + FIRST_WORD_ID
+        g = rng.gamma(alpha, 1.0, (n_topics, sub_vocab)) + 1e-12
+        g /= g.sum(1, keepdims=True)
+        cdf = np.cumsum(g, 1)
+        cdf[:, -1] = 1.0
+        # one global sorted array: row t lives in [t, t + 1)
+        self.flat_cdf = (cdf + np.arange(n_topics)[:, None]).reshape(-1)
+        zipf = 1.0 / np.arange(1, nwords + 1) ** 1.1
+        zipf /= zipf.sum()
+        self.zipf_cdf = np.cumsum(zipf)
+        self.zipf_cdf[-1] = 1.0
+        self.zipf_perm = rng.permutation(nwords).astype(np.int32) + FIRST_WORD_ID
+
+    def sample(self, n: int, seed: int, len_mean: float, len_std: float, len_min: int, len_max: int,
+               mix: float = 0.8) -> Corpus:
+        rng = np.random.default_rng(seed)
+        topics = rng.integers(0, self.n_topics, n).astype(np.int32)
+        lens = np.clip(np.rint(rng.normal(len_mean, len_std, n)), len_min, len_max).astype(np.int64)
+        offsets = np.zeros(n + 1, np.uint64)
+        offsets[1:] = np.cumsum(lens)
+        total = int(offsets[-1])
+        tok_topic = np.repeat(topics, lens)
+        u = rng.random(total)
+        from_topic = rng.random(total) < mix
+        tokens = np.empty(total, np.uint16)
+        # topic draws: one searchsorted over the concatenated CDFs
+        idx = np.searchsorted(self.flat_cdf, u[from_topic] + tok_topic[from_topic], side="right")
+        idx = np.minimum(idx, (tok_topic[from_topic] + 1) * self.sub_vocab - 1)
+        tokens[from_topic] = self.topic_words.reshape(-1)[idx]
+        zi = np.searchsorted(self.zipf_cdf, u[~from_topic], side="right")
+        tokens[~from_topic] = self.zipf_perm[np.minimum(zi, self.zipf_perm.size - 1)]
+        starts = offsets[:-1].astype(np.int64)
+        tokens[starts] = CLS_ID
+        tokens[starts + lens - 1] = SEP_ID
+        return Corpus(tokens, offsets, topics)
+
+
+def make_corpus(n: int, vocab_size: int = 30522, seed: int = 1234, max_len: int = 256, n_topics: int | None = None):
+    tm = TopicModel(vocab_size, n_topics or max(4, int(round(np.sqrt(n)))), seed)
+    corpus = tm.sample(n, seed + 1, 128, 48, 16, max_len)
+    return tm, corpus
+
+
+def make_queries(tm: TopicModel, nq: int, seed: int = 4321) -> Corpus:
+    return tm.sample(nq, seed, 24, 8, 4, 64)
