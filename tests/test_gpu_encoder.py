@@ -1,0 +1,54 @@
+"""Recompute stage end to end (token ids -> pooled, normalised embedding) against the fp32
+transformers.BertModel oracle on the same seeded weights."""
+import numpy as np
+import pytest
+
+from helpers import open_encoder_only
+from leann_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("preset,n", [(synth.TINY, 300), (synth.MINILM_L6, 48), (synth.BGE_BASE, 12)])
+def test_encoder_matches_fp32_bert(lib, cuda_ok, preset, n):
+    from oracle.encoder_oracle import EncoderOracle
+    w = synth.synthetic_weights(preset, 0)
+    _, corpus = synth.make_corpus(n, preset.vocab_size, seed=11, max_len=min(256, preset.max_pos))
+    idx = open_encoder_only(preset, synth.pack_weights(preset, w), corpus)
+    E = idx.encode_ids(np.arange(n))
+    ref = EncoderOracle(preset, w).encode_store(corpus.tokens, corpus.offsets)
+    assert np.isfinite(E).all()
+    assert np.allclose(np.linalg.norm(E, axis=1), 1, atol=1e-4)
+    assert np.abs(E - ref).max() < 2e-3, np.abs(E - ref).max()
+    # what the traversal consumes: distances -E.q  (hnsw_embedding_server.py:195-200), tolerance of north_star
+    q = ref[:8]
+    assert np.abs(E @ q.T - ref @ q.T).max() < 1e-3
+
+
+def test_encoding_is_batch_and_position_independent(lib, cuda_ok):
+    preset = synth.TINY
+    w = synth.synthetic_weights(preset, 1)
+    _, corpus = synth.make_corpus(500, preset.vocab_size, seed=3, max_len=preset.max_pos)
+    idx = open_encoder_only(preset, synth.pack_weights(preset, w), corpus)
+    all_ = idx.encode_ids(np.arange(500))
+    perm = np.random.default_rng(0).permutation(500)[:77]
+    some = idx.encode_ids(perm)
+    assert np.array_equal(some, all_[perm])  # bit-identical: a passage's embedding never depends on its batch
+    one = idx.encode_ids(np.array([perm[5]]))
+    assert np.array_equal(one[0], all_[perm[5]])
+    idx.configure(0, 64)  # smaller encoder passes
+    assert np.array_equal(idx.encode_ids(np.arange(500)), all_)
+
+
+def test_encode_tokens_equals_encode_ids_and_truncates(lib, cuda_ok):
+    preset = synth.TINY
+    w = synth.synthetic_weights(preset, 2)
+    _, corpus = synth.make_corpus(40, preset.vocab_size, seed=4, max_len=preset.max_pos)
+    idx = open_encoder_only(preset, synth.pack_weights(preset, w), corpus)
+    a = idx.encode_ids(np.arange(40))
+    b = idx.encode_tokens(corpus.tokens, corpus.offsets)
+    assert np.array_equal(a, b)
+    long_seq = np.concatenate([corpus.passage(0), corpus.passage(1), corpus.passage(2)])[: 3 * preset.max_pos]
+    t = idx.encode_tokens(long_seq.astype(np.uint16), np.array([0, long_seq.size], np.uint64))
+    t2 = idx.encode_tokens(long_seq[: preset.max_pos].astype(np.uint16), np.array([0, preset.max_pos], np.uint64))
+    assert np.array_equal(t, t2)  # truncation=True at max_seq_length

@@ -1,0 +1,81 @@
+"""Recompute-stage kernels against plain PyTorch fp32 references of the same op (called through
+the C-ABI test hooks with device pointers)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gelu(x):
+    return torch.nn.functional.gelu(x)
+
+
+@pytest.mark.parametrize("M", [1, 37, 128, 129, 1000, 4096 + 77, 148 * 128 * 3 + 5])
+@pytest.mark.parametrize("N,K", [(384, 384), (1152, 384), (1536, 384), (384, 1536)])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_tcgen05_vs_torch(lib, cuda_ok, M, N, K, epi):
+    if epi == 1 and N != 1536:
+        pytest.skip("GELU epilogue is only used for the FFN up-projection")
+    if epi == 2 and N != 384:
+        pytest.skip("residual epilogue is only used for the H-wide projections")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K + epi)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 1.0).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    res = torch.randn(M, N, device="cuda", generator=g).half()
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    rc = lib.lb2_test_gemm_f16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), res.data_ptr(), C.data_ptr(), M, N, K, epi)
+    assert rc == 0, lib.lb2_last_error()
+    ref = A.float() @ W.float().T + bias
+    if epi == 1:
+        ref = _gelu(ref)
+    if epi == 2:
+        ref = ref + res.float()
+    err = (C.float() - ref).abs()
+    tol = 2e-3 + 1.5e-3 * ref.abs()  # fp16 output rounding (2^-11 relative) + accumulation-order noise
+    assert torch.isfinite(C).all()
+    assert (err <= tol).all(), f"max err {err.max().item()} at {torch.nonzero(err > tol)[:3].tolist()}"
+
+
+def test_gemm_rejects_unsupported_shapes(lib, cuda_ok):
+    A = torch.zeros(8, 100, device="cuda", dtype=torch.float16)
+    rc = lib.lb2_test_gemm_f16(A.data_ptr(), A.data_ptr(), A.data_ptr(), A.data_ptr(), A.data_ptr(), 8, 100, 100, 0)
+    assert rc != 0 and b"unsupported shape" in lib.lb2_last_error()
+
+
+@pytest.mark.parametrize("H", [384, 768])
+@pytest.mark.parametrize("rows", [1, 7, 8, 1000])
+def test_layernorm_vs_torch(lib, cuda_ok, H, rows):
+    g = torch.Generator(device="cuda").manual_seed(rows + H)
+    x = (torch.randn(rows, H, device="cuda", generator=g) * 3 + 0.5).half()
+    gam = torch.randn(H, device="cuda", generator=g)
+    bet = torch.randn(H, device="cuda", generator=g)
+    out = torch.empty_like(x)
+    assert lib.lb2_test_layernorm_f16(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), out.data_ptr(), rows, H, 1e-12) == 0
+    ref = torch.nn.functional.layer_norm(x.float(), (H,), gam, bet, 1e-12)
+    assert (out.float() - ref).abs().max().item() <= 2e-3 + 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("H,heads", [(384, 12), (768, 12)])
+def test_attention_vs_torch(lib, cuda_ok, H, heads):
+    lens = [1, 2, 15, 16, 17, 63, 64, 65, 100, 128, 200, 255, 256]
+    T = sum(lens)
+    hd = H // heads
+    g = torch.Generator(device="cuda").manual_seed(H)
+    qkv = (torch.randn(T, 3 * H, device="cuda", generator=g) * 1.5).half()
+    ctx = torch.full((T, H), float("nan"), device="cuda", dtype=torch.float16)
+    hl = np.asarray(lens, np.int32)
+    rc = lib.lb2_test_attention_f16(qkv.data_ptr(), hl.ctypes.data, len(lens), H, heads, 256, ctx.data_ptr())
+    assert rc == 0, lib.lb2_last_error()
+    assert torch.isfinite(ctx).all()
+    off = 0
+    worst = 0.0
+    for L in lens:
+        blk = qkv[off:off + L].float()
+        q, k, v = (blk[:, i * H:(i + 1) * H].reshape(L, heads, hd).transpose(0, 1) for i in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / hd ** 0.5, dim=-1)
+        ref = (p @ v).transpose(0, 1).reshape(L, H)
+        worst = max(worst, (ctx[off:off + L].float() - ref).abs().max().item())
+        off += L
+    assert worst <= 4e-3, worst  # P is rounded to fp16 before P.V, output to fp16
