@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the selective-recompute HNSW search path (BASELINE.json metric:
+QPS @ recall@10, MiniLM-L6 384d, efSearch ("beam") = 64).
+
+    python bench.py --gpus N --steps K --warmup W             # this repo (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path, rank 0 only
+
+One "step" = one Searcher.search() pass over one batch of `--queries` synthetic queries per GPU
+(recompute mode: traversal + encoder forward for every hop's new nodes + scoring, k=10, ef=64).
+Set-up (untimed, synthetic, seeded): topic-structured token corpus -> passage embeddings with the
+GPU encoder -> HNSW-format graph (torch builder) written in the reference's CSR .index format ->
+index opened through the plugin backend.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "QPS @ recall@10 (HNSW selective recompute, all-MiniLM-L6-v2 384d, efSearch=64, k=10)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=int(os.environ.get("LB2_BENCH_CHUNKS", 1_000_000)))
+    ap.add_argument("--queries", type=int, default=int(os.environ.get("LB2_BENCH_QUERIES", 1024)), help="queries per step per GPU")
+    ap.add_argument("--ef", type=int, default=64)
+    ap.add_argument("--beam", type=int, default=1)
+    ap.add_argument("--ref-queries", type=int, default=int(os.environ.get("LB2_BENCH_REF_QUERIES", 2)), help="queries per CPU-reference step")
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 0)))
+    ap.add_argument("--per-pass", type=int, default=int(os.environ.get("LB2_PER_PASS", 0)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def log(*a):
+    if int(os.environ.get("RANK", 0)) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_world(args, rank, device):
+    """Untimed set-up.  Returns everything a step needs."""
+    import torch
+    from leann_b200 import capi, csr, synth
+    from leann_b200.graph_build import build_hnsw_graph
+
+    preset = synth.MINILM_L6
+    t0 = time.time()
+    weights = synth.synthetic_weights(preset, 0)
+    blob = synth.pack_weights(preset, weights)
+    tm, corpus = synth.make_corpus(args.chunks, preset.vocab_size, seed=1234, max_len=preset.max_pos)
+    n_steps_total = args.warmup + args.steps
+    world = max(1, args.gpus)
+    queries = synth.make_queries(tm, args.queries * n_steps_total * world, seed=4321)
+    log(f"corpus: {corpus.n} chunks, {corpus.tokens.size/1e6:.1f} M tokens, {tm.n_topics} topics ({time.time()-t0:.1f}s)")
+    work = Path(tempfile.mkdtemp(prefix=f"lb2_bench_r{rank}_"))
+    # 1. passage embeddings with the GPU encoder (stub graph: the encoder needs an open index handle)
+    from tests.helpers import stub_graph, write_leann_index
+    stub = work / "stub.index"
+    csr.write_compact_index(str(stub), stub_graph(corpus.n, preset.hidden))
+    enc = capi.Index(str(stub), device)
+    enc.set_passages(corpus.tokens, corpus.offsets)
+    enc.set_encoder(preset.config(), blob)
+    E = torch.empty((corpus.n, preset.hidden), dtype=torch.float32, device=f"cuda:{device}")
+    torch.cuda.synchronize()
+    t1 = time.time()
+    enc.encode_range_device(0, corpus.n, E.data_ptr())
+    torch.cuda.synchronize()
+    t_embed = time.time() - t1
+    lens = np.minimum(np.diff(corpus.offsets.astype(np.int64)), preset.max_pos)
+    embed_flops = float(sum(preset.flops_per_chunk(int(L)) * c for L, c in zip(*np.unique(lens, return_counts=True))))
+    log(f"embedded corpus in {t_embed:.1f}s = {embed_flops/t_embed/1e12:.0f} TFLOP/s algorithmic (encoder only)")
+    Q = enc.encode_tokens(queries.tokens, queries.offsets)
+    enc.close()
+    # 2. graph in the reference's CSR format
+    t2 = time.time()
+    g = build_hnsw_graph(E, M=32, metric="mips", device=f"cuda:{device}")
+    log(f"graph: {g.neighbors.size/1e6:.1f} M edges, max_level {g.max_level} ({time.time()-t2:.1f}s)")
+    index_path = write_leann_index(work, "bench", g, preset, corpus)
+    # 3. exact ground truth (brute-force fp32 IP over the same embeddings: run_evaluation.py:358-367 with k=10)
+    Qt = torch.from_numpy(Q).to(E.device)
+    gt = torch.empty((Qt.shape[0], 10), dtype=torch.int64, device=E.device)
+    for b0 in range(0, Qt.shape[0], 2048):
+        gt[b0:b0 + 2048] = torch.topk(Qt[b0:b0 + 2048] @ E.T, 10, dim=1).indices
+    gt = gt.cpu().numpy()
+    del E, Qt
+    torch.cuda.empty_cache()
+    return dict(preset=preset, weights=weights, corpus=corpus, graph=g, Q=Q, gt=gt, index_path=index_path, work=work,
+                embed_tflops=embed_flops / t_embed / 1e12)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("LB2_PROFILE_GEMM", "1")
+    from leann_b200 import backend, build, capi
+    from leann_b200.parallel import sharded_search
+    from tests.helpers import recall_at_k
+
+    if build.needs_build():
+        build.build()
+    W = build_world(args, rank, local)
+    searcher = backend.B200HnswBackend.searcher(str(W["index_path"]), device=local, slots=args.slots, passages_per_pass=args.per_pass)
+    port = searcher._ensure_server_running(str(W["index_path"]) + ".meta.json", 5557)
+    idx = searcher._index
+    nq, k = args.queries, 10
+    params = capi.make_params(args.ef, args.beam, 0, True, recompute=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+    dq = torch.empty((nq, W["preset"].hidden), dtype=torch.float32, device=f"cuda:{local}")
+    dD = torch.empty((nq, k), dtype=torch.float32, device=f"cuda:{local}")
+    dI = torch.empty((nq, k), dtype=torch.int64, device=f"cuda:{local}")
+    pinned_q = torch.empty((nq, W["preset"].hidden), dtype=torch.float32).pin_memory()
+
+    def batch(step):  # distinct queries for every (step, rank)
+        b0 = (step * world + rank) * nq
+        return W["Q"][b0:b0 + nq], W["gt"][b0:b0 + nq]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value`
+    for s in range(args.warmup):
+        q, _ = batch(s)
+        dq.copy_(torch.from_numpy(q))
+        flush.fill_(s & 0xFF)
+        idx.search_device(dq.data_ptr(), nq, k, dD.data_ptr(), dI.data_ptr(), params)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = dict(gpu_ms=0.0, encoder_ms=0.0, gemm_ms=0.0, gemm_flops=0.0, launches=0, ndis=0, nhops=0, n_recomputed=0,
+               n_requested=0, n_tokens=0, steps=0)
+    recalls = []
+    t_dev = 0.0
+    for s in range(args.warmup, args.warmup + args.steps):
+        q, gt = batch(s)
+        dq.copy_(torch.from_numpy(q))  # inputs resident in HBM before the timed region
+        flush.fill_(s & 0xFF)          # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        ev0.record()
+        idx.search_device(dq.data_ptr(), nq, k, dD.data_ptr(), dI.data_ptr(), params)
+        ev1.record()
+        torch.cuda.synchronize()
+        t_dev += ev0.elapsed_time(ev1) / 1e3
+        st = idx.last_stats
+        for key in ("gpu_ms", "encoder_ms", "gemm_ms", "gemm_flops", "ndis", "nhops", "n_recomputed", "n_requested", "n_tokens"):
+            agg[key] += getattr(st, key)
+        agg["launches"] += st.n_kernel_launches
+        agg["steps"] += st.n_steps
+        recalls.append(recall_at_k(dI.cpu().numpy(), gt))
+    barrier()
+    clk = clocks.stop()
+    t_all = torch.tensor([t_dev], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_max = float(t_all.item())
+    total_q = nq * args.steps * world
+    value = total_q / t_max
+
+    # ---------------- end-to-end arm through the plugin API: host query -> host labels/distances
+    t_e2e = 0.0
+    h2d = d2h = 0
+    for s in range(args.warmup, args.warmup + args.steps):
+        q, gt = batch(s)
+        pinned_q.copy_(torch.from_numpy(q))
+        flush.fill_(s & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            D, I = sharded_search(lambda qs: idx.search(qs, k, params), np.concatenate([pinned_q.numpy()] * 1), k)
+        else:
+            out = searcher.search(pinned_q.numpy(), k, zmq_port=port, complexity=args.ef, beam_width=args.beam,
+                                  recompute_embeddings=True)
+            D, I = out["distances"], out["labels"]
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        t_e2e += float(dt.item())
+        h2d += q.nbytes
+        d2h += nq * k * (4 + 8)
+    e2e_value = total_q / t_e2e
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained, cuBLAS bf16 sustained)" if peaks else "fallback 1590"
+        gemm_tf = agg["gemm_flops"] / (agg["gemm_ms"] / 1e3) / 1e12 if agg["gemm_ms"] > 0 else None
+        lens = np.minimum(np.diff(W["corpus"].offsets.astype(np.int64)), W["preset"].max_pos)
+        out = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (fp32 accumulate; fp32 scoring)", "data": "synthetic",
+            "config": {"workload": f"{args.chunks} synthetic chunks (mean {lens.mean():.0f} tokens), all-MiniLM-L6-v2 384d "
+                                   f"architecture with seeded synthetic weights, HNSW M=32 recompute, efSearch={args.ef}, "
+                                   f"beam_width={args.beam}, k=10, {nq} queries/step/GPU",
+                       "l2": "256 MiB flush buffer written between timed steps; working set (graph+passages) > L2",
+                       "parallelism": f"queries sharded over {world} GPU(s), graph/passages/encoder replicated, one NCCL all_gather of results"},
+            "recall_at_10": float(np.mean(recalls)),
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": int(agg["launches"]),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05)", "achieved": gemm_tf, "peak": peak,
+                         "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "share_of_step": agg["gemm_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None},
+            "detail": {"ndis_per_query": agg["ndis"] / (nq * args.steps), "nhops_per_query": agg["nhops"] / (nq * args.steps),
+                       "recomputed_per_query": agg["n_recomputed"] / (nq * args.steps),
+                       "dedup_saving": 1 - agg["n_recomputed"] / max(1, agg["n_requested"]),
+                       "tokens_per_query": agg["n_tokens"] / (nq * args.steps),
+                       "traversal_steps_per_call": agg["steps"] / args.steps,
+                       "encoder_share": agg["encoder_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None,
+                       "encoder_algorithmic_tflops": (agg["n_tokens"] * 0 + _encoder_flops(W, agg)) / (agg["encoder_ms"] / 1e3) / 1e12 if agg["encoder_ms"] else None,
+                       "corpus_embed_tflops": W["embed_tflops"]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_reference(W, args, max(1, args.ref_queries), 1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def _encoder_flops(W, agg):
+    # algorithmic F(L) summed over the recomputed passages ~= tokens * per-token linear flops + attention term
+    p = W["preset"]
+    mean_len = agg["n_tokens"] / max(1, agg["n_recomputed"])
+    return agg["n_recomputed"] * p.flops_per_chunk(int(round(mean_len)))
+
+
+def cpu_reference(W, args, n_queries, steps):
+    """The reference's own CPU path on this box's host cores: the faiss-fork traversal compiled from
+    /root/reference (oracle/_ref, prebuilt) — or the C restatement when that library is absent — with
+    distances_batch served by a torch-CPU fp32 BertModel forward + numpy scoring, exactly the
+    embedding server's distance branch (hnsw_embedding_server.py:147-211), queries one at a time like
+    the single REP loop."""
+    import torch
+    from oracle.binding import Oracle, Reference, have_reference
+    from oracle.encoder_oracle import EncoderOracle
+    from tests.helpers import recall_at_k
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    eo = EncoderOracle(W["preset"], W["weights"])
+    fn = eo.distance_fn(W["corpus"].tokens, W["corpus"].offsets, True, batch_size=64)
+    kind = "reference" if have_reference() else "port"
+    trav = Reference.from_csr(W["graph"], None, M=32) if kind == "reference" else Oracle(W["graph"])
+    q = W["Q"][: n_queries * steps]
+    t0 = time.perf_counter()
+    D, I, ndis, nhops = trav.search(q, 10, ef=args.ef, beam=args.beam, dist_fn=fn, nthreads=1)
+    dt = time.perf_counter() - t0
+    return {"value": len(q) / dt, "unit": "queries/s", "cores": cores, "kind": kind,
+            "sample": f"{len(q)} queries of the same workload, serial, torch intra-op threads={cores}, "
+                      f"{float(ndis.mean()):.0f} recomputes/query",
+            "recall_at_10": recall_at_k(I, W["gt"][: len(q)]), "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "set-up (corpus embedding + graph) needs the GPU encoder; no GPU here"}))
+        return
+    from leann_b200 import build
+    if build.needs_build():
+        build.build()
+    args_local = argparse.Namespace(**vars(args))
+    args_local.gpus = 1
+    W = build_world(args_local, 0, 0)
+    n = max(1, args.ref_queries)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(W, args, 1, 1)
+    t0 = time.perf_counter()
+    res = cpu_reference(W, args, n, max(1, args.steps))
+    dt = time.perf_counter() - t0
+    lens = np.minimum(np.diff(W["corpus"].offsets.astype(np.int64)), W["preset"].max_pos)
+    out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "queries/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CPU)", "data": "synthetic",
+           "config": {"workload": f"{args.chunks} synthetic chunks (mean {lens.mean():.0f} tokens), all-MiniLM-L6-v2 384d "
+                                  f"architecture with seeded synthetic weights, HNSW M=32 recompute, efSearch={args.ef}, "
+                                  f"beam_width={args.beam}, k=10, {n} queries/step (bounded sample)"},
+           "recall_at_10": res["recall_at_10"],
+           "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

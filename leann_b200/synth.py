@@ -106,6 +106,27 @@ class Corpus:
         return self.tokens[int(self.offsets[i]): int(self.offsets[i + 1])]
 
 
+def _searchsorted_right(sorted_f64: np.ndarray, values_f64: np.ndarray) -> np.ndarray:
+    """np.searchsorted(side='right'); large inputs go through torch on the GPU when there is one
+    (identical result: exact float64 comparisons), because 10^8 cache-missing binary searches
+    take a minute on the host."""
+    if values_f64.size > (1 << 22):
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                a = torch.from_numpy(np.ascontiguousarray(sorted_f64)).cuda()
+                out = np.empty(values_f64.size, np.int64)
+                step = 1 << 26
+                for b0 in range(0, values_f64.size, step):
+                    v = torch.from_numpy(np.ascontiguousarray(values_f64[b0:b0 + step])).cuda()
+                    out[b0:b0 + step] = torch.searchsorted(a, v, right=True).cpu().numpy()
+                return out
+        except Exception:
+            pass
+    return np.searchsorted(sorted_f64, values_f64, side="right")
+
+
 class TopicModel:
     """K topics over a vocabulary; shared by the corpus and the query generator."""
 
@@ -143,10 +164,10 @@ class TopicModel:
         from_topic = rng.random(total) < mix
         tokens = np.empty(total, np.uint16)
         # topic draws: one searchsorted over the concatenated CDFs
-        idx = np.searchsorted(self.flat_cdf, u[from_topic] + tok_topic[from_topic], side="right")
+        idx = _searchsorted_right(self.flat_cdf, u[from_topic] + tok_topic[from_topic])
         idx = np.minimum(idx, (tok_topic[from_topic] + 1) * self.sub_vocab - 1)
         tokens[from_topic] = self.topic_words.reshape(-1)[idx]
-        zi = np.searchsorted(self.zipf_cdf, u[~from_topic], side="right")
+        zi = _searchsorted_right(self.zipf_cdf, u[~from_topic])
         tokens[~from_topic] = self.zipf_perm[np.minimum(zi, self.zipf_perm.size - 1)]
         starts = offsets[:-1].astype(np.int64)
         tokens[starts] = CLS_ID
