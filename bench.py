@@ -107,7 +107,7 @@ def build_world(args, rank, device):
     log(f"corpus: {corpus.n} chunks, {corpus.tokens.size/1e6:.1f} M tokens, {tm.n_topics} topics ({time.time()-t0:.1f}s)")
     work = Path(tempfile.mkdtemp(prefix=f"lb2_bench_r{rank}_"))
     # 1. passage embeddings with the GPU encoder (stub graph: the encoder needs an open index handle)
-    from tests.helpers import stub_graph, write_leann_index
+    from leann_b200.tooling import stub_graph, write_leann_index
     stub = work / "stub.index"
     csr.write_compact_index(str(stub), stub_graph(corpus.n, preset.hidden))
     enc = capi.Index(str(stub), device)
@@ -154,7 +154,7 @@ def run_b200(args):
     os.environ.setdefault("LB2_PROFILE_GEMM", "1")
     from leann_b200 import backend, build, capi
     from leann_b200.parallel import sharded_search
-    from tests.helpers import recall_at_k
+    from leann_b200.tooling import recall_at_k
 
     if build.needs_build():
         build.build()
@@ -229,7 +229,10 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         if world > 1:
-            D, I = sharded_search(lambda qs: idx.search(qs, k, params), np.concatenate([pinned_q.numpy()] * 1), k)
+            # the global batch of this step = every rank's queries; sharded_search gives each rank its
+            # contiguous slice and all_gathers (labels, distances) over NCCL at the end
+            q_glob = W["Q"][s * world * nq:(s + 1) * world * nq]
+            D, I = sharded_search(lambda qs: idx.search(np.ascontiguousarray(qs), k, params), q_glob, k)
         else:
             out = searcher.search(pinned_q.numpy(), k, zmq_port=port, complexity=args.ef, beam_width=args.beam,
                                   recompute_embeddings=True)
@@ -305,7 +308,7 @@ def cpu_reference(W, args, n_queries, steps):
     import torch
     from oracle.binding import Oracle, Reference, have_reference
     from oracle.encoder_oracle import EncoderOracle
-    from tests.helpers import recall_at_k
+    from leann_b200.tooling import recall_at_k
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
