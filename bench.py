@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--queries", type=int, default=int(os.environ.get("LB2_BENCH_QUERIES", 1024)), help="queries per step per GPU")
     ap.add_argument("--ef", type=int, default=64)
     ap.add_argument("--beam", type=int, default=1)
-    ap.add_argument("--ref-queries", type=int, default=int(os.environ.get("LB2_BENCH_REF_QUERIES", 2)), help="queries per CPU-reference step")
+    ap.add_argument("--ref-queries", type=int, default=int(os.environ.get("LB2_BENCH_REF_QUERIES", 1)), help="queries per CPU-reference step")
     ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 0)))
     ap.add_argument("--per-pass", type=int, default=int(os.environ.get("LB2_PER_PASS", 0)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,9 +310,21 @@ def cpu_reference(W, args, n_queries, steps):
     from oracle.encoder_oracle import EncoderOracle
     from leann_b200.tooling import recall_at_k
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     eo = EncoderOracle(W["preset"], W["weights"])
+    # The reference caps torch at min(8, cores) (embedding_compute.py:150).  A hop's batch is ~20 short
+    # sequences, so more threads do not always help: calibrate on one hop-sized batch and keep the fastest.
+    probe_ids = list(range(24))
+    best, cores = None, 1
+    for th in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), min(64, ncpu)}):
+        torch.set_num_threads(th)
+        eo.encode_store(W["corpus"].tokens, W["corpus"].offsets, probe_ids, 64)
+        t0 = time.perf_counter()
+        eo.encode_store(W["corpus"].tokens, W["corpus"].offsets, probe_ids, 64)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, th
+    torch.set_num_threads(cores)
     fn = eo.distance_fn(W["corpus"].tokens, W["corpus"].offsets, True, batch_size=64)
     kind = "reference" if have_reference() else "port"
     trav = Reference.from_csr(W["graph"], None, M=32) if kind == "reference" else Oracle(W["graph"])
@@ -321,7 +333,8 @@ def cpu_reference(W, args, n_queries, steps):
     D, I, ndis, nhops = trav.search(q, 10, ef=args.ef, beam=args.beam, dist_fn=fn, nthreads=1)
     dt = time.perf_counter() - t0
     return {"value": len(q) / dt, "unit": "queries/s", "cores": cores, "kind": kind,
-            "sample": f"{len(q)} queries of the same workload, serial, torch intra-op threads={cores}, "
+            "sample": f"{len(q)} queries of the same workload, serial (single embedding server), torch intra-op "
+                      f"threads={cores} of {ncpu} host cores (fastest of 8/16/32/64 on a hop-sized batch), "
                       f"{float(ndis.mean()):.0f} recomputes/query",
             "recall_at_10": recall_at_k(I, W["gt"][: len(q)]), "seconds": dt}
 
