@@ -133,8 +133,9 @@ layernorm_kernel(const __half* __restrict__ in, const float* __restrict__ g, con
 
 // ---------------------------------------------------------------------------------------
 // Self-attention, one CTA per (sequence, head): softmax(Q K^T / sqrt(hd)) V, no padding keys.
-// K and V^T of the head are staged once in shared memory; each warp owns 16-query tiles and
-// walks the keys in blocks of 64 with an online softmax (fp32 statistics), mma.sync m16n8k16.
+// K and V of the head are staged once in shared memory (row-major, 16-byte copies); each warp owns
+// 16-query tiles and walks the keys in blocks of 64 with an online softmax (fp32 statistics,
+// ex2.approx), mma.sync m16n8k16 with ldmatrix / ldmatrix.trans operand fragments.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -147,6 +148,22 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128)
 attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq_start,
@@ -157,45 +174,44 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq
     const int L = passage_len(tok_off, seq_node[s], max_pos);
     const int row0 = seq_start[s] - row_base;
     const int ld = 3 * hidden;
-    constexpr int KP = HD + 8;             // K row pitch (halves): conflict-free b-fragment reads
-    const int Lp = (L + 63) & ~63;         // keys padded to the 64-key block
-    const int VP = Lp + 8;                 // V^T row pitch (halves)
-    __half* Ks = reinterpret_cast<__half*>(att_smem);       // [Lp][KP]
-    __half* Vt = Ks + static_cast<size_t>(Lp) * KP;          // [HD][VP]
+    constexpr int P = HD + 8;               // row pitch in halves: 16-byte aligned rows, conflict-free ldmatrix
+    const int Lp = (L + 63) & ~63;          // keys padded to the 64-key block
+    __half* Ks = reinterpret_cast<__half*>(att_smem);  // [Lp][P]
+    __half* Vs = Ks + static_cast<size_t>(Lp) * P;     // [Lp][P]
     const __half* qbase = qkv + static_cast<size_t>(row0) * ld + h * HD;
     const __half* kbase = qbase + hidden;
     const __half* vbase = qbase + 2 * hidden;
 
-    // stage K (row-major) and V (transposed); zero the padded keys
+    // stage K and V row-major with 16-byte copies; padded keys are zero
     for (int idx = threadIdx.x; idx < Lp * (HD / 8); idx += blockDim.x) {
         const int key = idx / (HD / 8), c8 = (idx % (HD / 8)) * 8;
         uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
         if (key < L) {
-            kv = *reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(key) * ld + c8);
-            vv = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * ld + c8);
+            kv = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(key) * ld + c8));
+            vv = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * ld + c8));
         }
-        *reinterpret_cast<uint4*>(Ks + key * KP + c8) = kv;
-        const __half* vh = reinterpret_cast<const __half*>(&vv);
-#pragma unroll
-        for (int j = 0; j < 8; j++) Vt[(c8 + j) * VP + key] = vh[j];
+        *reinterpret_cast<uint4*>(Ks + key * P + c8) = kv;
+        *reinterpret_cast<uint4*>(Vs + key * P + c8) = vv;
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const float scale_log2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
+    // ldmatrix row addressing: lanes 0-7 / 8-15 / 16-23 / 24-31 supply the rows of matrices 0..3
+    const int lm_row = lane & 7, lm_mat = lane >> 3;
 
     for (int q0 = warp * 16; q0 < L; q0 += 64) {
-        // Q fragments (A operand), rows q0+g and q0+g+8
+        // Q fragments (A operand), rows q0+g and q0+g+8, straight from global (64 B per row)
         uint32_t qa[HD / 16][4];
         const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ks++) {
             const int c = ks * 16 + 2 * t;
-            qa[ks][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c) : 0u;
-            qa[ks][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c) : 0u;
-            qa[ks][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c + 8) : 0u;
-            qa[ks][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c + 8) : 0u;
+            qa[ks][0] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c)) : 0u;
+            qa[ks][1] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c)) : 0u;
+            qa[ks][2] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c + 8)) : 0u;
+            qa[ks][3] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c + 8)) : 0u;
         }
         float o[HD / 8][4];
 #pragma unroll
@@ -203,19 +219,20 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq
         float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
         for (int kb = 0; kb < Lp; kb += 64) {
+            // ---- S = Q K^T for 64 keys: B fragments of K^T are plain ldmatrix tiles of row-major K
             float sc[8][4];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
                 sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-                const __half* kr = Ks + (kb + nt * 8 + g) * KP + 2 * t;
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ks++) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-                    mma_16816(sc[nt], qa[ks], b0, b1);
+                for (int kp = 0; kp < HD / 32; kp++) {  // one x4 = (b0,b1) of two consecutive k-steps
+                    uint32_t b[4];
+                    ldsm_x4(b, Ks + (kb + nt * 8 + lm_row) * P + kp * 32 + lm_mat * 8);
+                    mma_16816(sc[nt], qa[2 * kp], b[0], b[1]);
+                    mma_16816(sc[nt], qa[2 * kp + 1], b[2], b[3]);
                 }
             }
-            // mask padded keys, running max
+            // ---- mask padded keys, running max
             float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
@@ -229,15 +246,16 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq
             bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
             bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
             bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-            const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);  // finite: key 0 of block 0 is valid
-            const float corr0 = exp2f((m0 - nm0) * scale_log2), corr1 = exp2f((m1 - nm1) * scale_log2);
+            const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);  // finite: every block holds a valid key
+            const float corr0 = fast_exp2((m0 - nm0) * scale_log2), corr1 = fast_exp2((m1 - nm1) * scale_log2);
             m0 = nm0; m1 = nm1;
+            const float ms0 = m0 * scale_log2, ms1 = m1 * scale_log2;
             float rs0 = 0.f, rs1 = 0.f;
             uint32_t pa[4][4];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
-                const float p0 = exp2f((sc[nt][0] - m0) * scale_log2), p1 = exp2f((sc[nt][1] - m0) * scale_log2);
-                const float p2 = exp2f((sc[nt][2] - m1) * scale_log2), p3 = exp2f((sc[nt][3] - m1) * scale_log2);
+                const float p0 = fast_exp2(fmaf(sc[nt][0], scale_log2, -ms0)), p1 = fast_exp2(fmaf(sc[nt][1], scale_log2, -ms0));
+                const float p2 = fast_exp2(fmaf(sc[nt][2], scale_log2, -ms1)), p3 = fast_exp2(fmaf(sc[nt][3], scale_log2, -ms1));
                 rs0 += p0 + p1; rs1 += p2 + p3;
                 const int kk = nt >> 1;
                 if ((nt & 1) == 0) { pa[kk][0] = pack_h2(p0, p1); pa[kk][1] = pack_h2(p2, p3); }
@@ -245,14 +263,17 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq
             }
             l0 = l0 * corr0 + rs0; l1 = l1 * corr1 + rs1;
 #pragma unroll
-            for (int dt = 0; dt < HD / 8; dt++) {
-                o[dt][0] *= corr0; o[dt][1] *= corr0; o[dt][2] *= corr1; o[dt][3] *= corr1;
-                const __half* vr = Vt + (dt * 8 + g) * VP + kb + 2 * t;
+            for (int dt = 0; dt < HD / 8; dt++) { o[dt][0] *= corr0; o[dt][1] *= corr0; o[dt][2] *= corr1; o[dt][3] *= corr1; }
+            // ---- O += P V: B fragments of row-major V come from transposed ldmatrix tiles
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr + kk * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + kk * 16 + 8);
-                    mma_16816(o[dt], pa[kk], b0, b1);
+            for (int kk = 0; kk < 4; kk++) {       // 16 keys per k-step
+#pragma unroll
+                for (int dp = 0; dp < HD / 16; dp++) {  // one x4.trans = (b0,b1) for two 8-wide d tiles
+                    uint32_t b[4];
+                    // matrices: 0 -> keys +0..7, d tile 2dp ; 1 -> keys +8..15, d tile 2dp ; 2,3 -> d tile 2dp+1
+                    ldsm_x4_trans(b, Vs + (kb + kk * 16 + (lm_mat & 1) * 8 + lm_row) * P + (2 * dp + (lm_mat >> 1)) * 8);
+                    mma_16816(o[2 * dp], pa[kk], b[0], b[1]);
+                    mma_16816(o[2 * dp + 1], pa[kk], b[2], b[3]);
                 }
             }
         }
@@ -351,7 +372,7 @@ bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_star
     if (n_seq <= 0) return true;
     const int hd = hidden / heads;
     const int Lp = (max_pos + 63) & ~63;
-    const size_t smem = (static_cast<size_t>(Lp) * (hd + 8) + static_cast<size_t>(hd) * (Lp + 8)) * sizeof(__half);
+    const size_t smem = 2 * static_cast<size_t>(Lp) * (hd + 8) * sizeof(__half);
     dim3 grid(n_seq, heads);
     if (hd == 32) {
         static bool set32 = false;
