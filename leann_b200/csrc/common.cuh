@@ -22,7 +22,8 @@ void set_error(const char* fmt, ...);
 enum Epilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2 };
 
 // ---- gemm_tcgen05.cu
-bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols = 64);
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms);
 int gemm_block_n();

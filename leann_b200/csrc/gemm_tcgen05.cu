@@ -11,7 +11,8 @@
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=192, K=16)
 //   warp 2        : TMEM allocator (2 accumulator stages x 192 columns -> 512 columns)
 //   warps 4..11   : epilogue       (tcgen05.ld 32x32b, register double-buffered -> bias / GELU /
-//                                   residual -> fp16 -> global); two warps per TMEM lane quarter
+//                                   residual -> fp16 -> swizzled smem box -> TMA store; residual tiles
+//                                   arrive by TMA load); two warps per TMEM lane quarter
 // Pipelines: smem full/empty mbarriers between TMA and MMA, TMEM full/empty mbarriers
 // between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
 // M is ragged (varlen-packed tokens): TMA zero-fills rows past M, stores are row-masked.
@@ -35,8 +36,12 @@ struct GemmSmem {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
+    // epilogue staging: per epilogue warp, one 32-row x 32-column fp16 box (2 KB, SWIZZLE_64B) per column chunk
+    static constexpr int EPI_CHUNKS = BLOCK_N / 32 / 2;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_CHUNKS * 2048;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024 /*alignment slack*/;
 };
 
 // HF "gelu" (erf form: x * Phi(x)), the activation of all-MiniLM-L6-v2 / bge-base BERT blocks.
@@ -57,8 +62,8 @@ __device__ __forceinline__ float gelu_fast(float x) {
 template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   __half* __restrict__ C, const float* __restrict__ bias, const __half* __restrict__ residual,
-                   int M, int N, int K) {
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+                   const float* __restrict__ bias, int M, int N, int K) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                             : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -71,7 +76,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;  // [EPI_WARPS] residual boxes landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -83,6 +89,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_c);
+        if (EPI == EPI_BIAS_RES) ptx::prefetch_tmap(&tmap_r);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; i++) {
@@ -93,6 +101,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::mbar_init(&tmem_full[i], 1);
             ptx::mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrive per epilogue warp
         }
+        for (int i = 0; i < EPI_WARPS; i++) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -153,66 +162,101 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the tile's columns =====
+        // ===== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the tile's columns.
+        // Per 32-column chunk: TMEM -> registers -> (+bias, GELU | +residual) -> fp16 -> this warp's
+        // private 32x32 smem box (SWIZZLE_64B, conflict-free 16-byte stores) -> TMA store.  The
+        // residual boxes of the tile are TMA-loaded into the same smem boxes before the accumulator
+        // is ready and overwritten in place.  Rows past M are clipped / zero-filled by TMA.
         const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
-        const int half = (warp - 4) >> 2;      // column half of the accumulator
-        constexpr int NCH = BLOCK_N / 32 / 2;  // 32-column chunks per warp
+        const int ew = warp - 4;
+        const int half = ew >> 2;              // column half of the accumulator
+        constexpr int NCH = L::EPI_CHUNKS;     // 32-column chunks per warp
+        uint8_t* stage_buf = smem + L::EPI_OFFSET + ew * NCH * 2048;
+        // swizzle-64B: the 16-byte chunk j of box row r lives at chunk j ^ ((r >> 1) & 3)
+        const int swz = (lane >> 1) & 3;
+        uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            const int row0 = m_blk * BLOCK_M + quarter * 32;
+            const int colbase = n_blk * BLOCK_N + half * NCH * 32;
+            if (EPI == EPI_BIAS_RES) {
+                if (lane == 0) {
+                    ptx::bulk_wait_read<0>();  // previous tile's stores no longer read the boxes
+                    ptx::mbar_expect_tx(&res_bar[ew], NCH * 2048);
+#pragma unroll
+                    for (int c = 0; c < NCH; c++)
+                        ptx::tma_load_2d(stage_buf + c * 2048, &tmap_r, &res_bar[ew], colbase + c * 32, row0);
+                }
+            }
             ptx::mbar_wait(&tmem_full[as], aphase);
             ptx::tc_fence_after();
-            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + half * NCH * 32;
-            const int colbase = n_blk * BLOCK_N + half * NCH * 32;
             uint32_t r[2][32];
             ptx::tmem_ld_32x32(taddr, r[0]);
+            if (EPI == EPI_BIAS_RES) {
+                ptx::mbar_wait(&res_bar[ew], res_phase);
+                res_phase ^= 1;
+            }
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
                 ptx::tmem_ld_wait();
                 if (c + 1 < NCH) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);  // overlaps the math below
                 const uint32_t(&acc)[32] = r[c & 1];
                 const int col0 = colbase + c * 32;
-                if (row < M) {
-                    const size_t off = static_cast<size_t>(row) * N + col0;
-                    uint4 resv[4];
+                uint8_t* box = stage_buf + c * 2048 + lane * 64;
+                if (EPI != EPI_BIAS_RES) {
+                    // the store issued from this box one tile ago must have finished reading it
+                    if (lane == 0) ptx::bulk_wait_read<NCH - 1>();
+                    __syncwarp();
+                }
+                const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {  // 16-byte piece j4 of this thread's 64-byte row segment
+                    uint4* slot = reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4));
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const float4 b4 = __ldg(bp + 2 * j4 + u);  // warp-uniform address: one broadcast transaction
+                        v[4 * u + 0] = __uint_as_float(acc[8 * j4 + 4 * u + 0]) + b4.x;
+                        v[4 * u + 1] = __uint_as_float(acc[8 * j4 + 4 * u + 1]) + b4.y;
+                        v[4 * u + 2] = __uint_as_float(acc[8 * j4 + 4 * u + 2]) + b4.z;
+                        v[4 * u + 3] = __uint_as_float(acc[8 * j4 + 4 * u + 3]) + b4.w;
+                    }
+                    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v[u] = gelu_fast(v[u]);
+                    }
                     if (EPI == EPI_BIAS_RES) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(residual + off);
+                        const uint4 rv = *slot;
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) resv[j] = __ldg(rp + j);
-                    }
-                    uint4 outv[4];
-                    __half2* oh = reinterpret_cast<__half2*>(outv);
-                    const __half2* rh = reinterpret_cast<const __half2*>(resv);
-                    const float4* bp = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 b4 = __ldg(bp + j);  // warp-uniform address: one broadcast transaction
-                        float v0 = __uint_as_float(acc[4 * j]) + b4.x;
-                        float v1 = __uint_as_float(acc[4 * j + 1]) + b4.y;
-                        float v2 = __uint_as_float(acc[4 * j + 2]) + b4.z;
-                        float v3 = __uint_as_float(acc[4 * j + 3]) + b4.w;
-                        if (EPI == EPI_BIAS_GELU) {
-                            v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3);
+                        for (int u = 0; u < 4; u++) {
+                            const float2 rf = __half22float2(rh[u]);
+                            v[2 * u] += rf.x;
+                            v[2 * u + 1] += rf.y;
                         }
-                        if (EPI == EPI_BIAS_RES) {
-                            const float2 ra = __half22float2(rh[2 * j]), rb = __half22float2(rh[2 * j + 1]);
-                            v0 += ra.x; v1 += ra.y; v2 += rb.x; v3 += rb.y;
-                        }
-                        oh[2 * j] = __floats2half2_rn(v0, v1);
-                        oh[2 * j + 1] = __floats2half2_rn(v2, v3);
                     }
-                    uint4* cp = reinterpret_cast<uint4*>(C + off);
+                    uint4 ov;
+                    __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) cp[j] = outv[j];
+                    for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+                    *slot = ov;
+                }
+                ptx::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmap_c, stage_buf + c * 2048, col0, row0);
+                    ptx::bulk_commit();
                 }
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
         }
+        if (lane == 0) ptx::bulk_wait_all();
     }
 
     ptx::tc_fence_before();
@@ -241,8 +285,10 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-// Row-major [rows, cols] fp16 matrix, box = [box_rows, 64 cols], 128B swizzle.
-bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// Row-major [rows, cols] fp16 matrix, box = [box_rows, box_cols]; box_cols = 64 -> SWIZZLE_128B
+// (MMA operand tiles), box_cols = 32 -> SWIZZLE_64B (epilogue boxes).
+bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -250,10 +296,11 @@ bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
     }
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {BLOCK_K, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows,
@@ -267,8 +314,8 @@ constexpr int GEMM_BLOCK_N = 192;
 constexpr int GEMM_STAGES = 4;
 
 template <int EPI>
-static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, __half* C,
-                               const float* bias, const __half* residual, int M, int N, int K, int num_sms) {
+static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                               const CUtensorMap& tr, const float* bias, int M, int N, int K, int num_sms) {
     using L = GemmSmem<GEMM_BLOCK_N, GEMM_STAGES>;
     auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI>;
     static bool attr_set = false;
@@ -279,7 +326,7 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, C, bias, residual, M, N, K);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K);
     return cudaGetLastError();
 }
 
@@ -291,17 +338,23 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
         set_error("gemm_f16: unsupported shape N=%d K=%d (need N%%192==0, K%%64==0)", N, K);
         return false;
     }
-    CUtensorMap ta, tb_local;
-    if (!make_tmap_f16_2d(&ta, A, (uint64_t)M, (uint64_t)K, BLOCK_M)) return false;
+    if (epi == EPI_BIAS_RES && !residual) {
+        set_error("gemm_f16: residual epilogue without a residual matrix");
+        return false;
+    }
+    CUtensorMap ta, tb_local, tc, tr;
+    if (!make_tmap_f16_2d(&ta, A, (uint64_t)M, (uint64_t)K, BLOCK_M, BLOCK_K)) return false;
+    if (!make_tmap_f16_2d(&tc, C, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
+    if (!make_tmap_f16_2d(&tr, epi == EPI_BIAS_RES ? residual : C, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
     if (!tmap_w) {
-        if (!make_tmap_f16_2d(&tb_local, W, (uint64_t)N, (uint64_t)K, GEMM_BLOCK_N)) return false;
+        if (!make_tmap_f16_2d(&tb_local, W, (uint64_t)N, (uint64_t)K, GEMM_BLOCK_N, BLOCK_K)) return false;
         tmap_w = &tb_local;
     }
     cudaError_t e;
     switch (epi) {
-        case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, C, bias, residual, M, N, K, num_sms); break;
-        case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, C, bias, residual, M, N, K, num_sms); break;
-        case EPI_BIAS_RES: e = launch_gemm<EPI_BIAS_RES>(stream, ta, *tmap_w, C, bias, residual, M, N, K, num_sms); break;
+        case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
+        case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
+        case EPI_BIAS_RES: e = launch_gemm<EPI_BIAS_RES>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
         default: set_error("gemm_f16: bad epilogue %d", epi); return false;
     }
     if (e != cudaSuccess) {
