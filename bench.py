@@ -38,11 +38,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=int(os.environ.get("LB2_BENCH_CHUNKS", 1_000_000)))
-    ap.add_argument("--queries", type=int, default=int(os.environ.get("LB2_BENCH_QUERIES", 1024)), help="queries per step per GPU")
+    ap.add_argument("--queries", type=int, default=int(os.environ.get("LB2_BENCH_QUERIES", 2048)), help="queries per step per GPU")
     ap.add_argument("--ef", type=int, default=64)
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--ref-queries", type=int, default=int(os.environ.get("LB2_BENCH_REF_QUERIES", 1)), help="queries per CPU-reference step")
-    ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 0)))
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 1024)))
     ap.add_argument("--per-pass", type=int, default=int(os.environ.get("LB2_PER_PASS", 0)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
