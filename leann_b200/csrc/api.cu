@@ -310,7 +310,7 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     S = (int)std::min<int64_t>(S, nq);
     S = std::max(S, 1);
     if (!ensure_state(x, S, tp, recompute)) return LB2_ERR_CUDA;
-    if (recompute && !encoder_reserve(&x->enc, (int64_t)x->per_pass * x->enc.cfg.max_pos)) return LB2_ERR_CUDA;
+    if (recompute && !encoder_reserve(&x->enc, (int64_t)x->per_pass * x->enc.cfg.max_pos, x->per_pass)) return LB2_ERR_CUDA;
 
     TravState& s = x->st;
     s.queries = d_q; s.nq = nq; s.outD = d_D; s.outI = d_I; s.out_ndis = x->d_qndis; s.out_nhops = x->d_qnhops;
@@ -402,7 +402,7 @@ int encode_impl(lb2_index* x, const uint16_t* d_tok, const uint64_t* d_off, cons
     if (!x->enc.loaded) { set_error("no encoder loaded"); return LB2_ERR_STATE; }
     const int H = x->enc.cfg.hidden, maxp = x->enc.cfg.max_pos;
     const int pp = x->per_pass;
-    if (!encoder_reserve(&x->enc, (int64_t)pp * maxp)) return LB2_ERR_CUDA;
+    if (!encoder_reserve(&x->enc, (int64_t)pp * maxp, pp)) return LB2_ERR_CUDA;
     if (!ensure_enc_scratch(x, pp)) return LB2_ERR_CUDA;
     std::vector<int> nodes(pp), starts(pp);
     for (int64_t base = 0; base < n; base += pp) {
@@ -664,18 +664,16 @@ int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, vo
 
 int lb2_test_attention_f16(const void* dqkv, const int32_t* h_seq_len, int n_seq, int hidden, int heads, int max_len,
                            void* dctx) {
-    std::vector<int> start((size_t)n_seq), node((size_t)n_seq);
-    std::vector<uint64_t> off((size_t)n_seq + 1, 0);
-    for (int i = 0; i < n_seq; i++) { start[i] = (int)off[i]; node[i] = i; off[i + 1] = off[i] + (uint64_t)h_seq_len[i]; }
-    int *ds = nullptr, *dn = nullptr;
-    uint64_t* doff = nullptr;
-    if (!dev_alloc(&ds, (size_t)n_seq) || !dev_alloc(&dn, (size_t)n_seq) || !dev_alloc(&doff, (size_t)n_seq + 1)) return LB2_ERR_CUDA;
+    std::vector<int> start((size_t)n_seq);
+    int acc = 0;
+    for (int i = 0; i < n_seq; i++) { start[i] = acc; acc += h_seq_len[i]; }
+    int *ds = nullptr, *dl = nullptr;
+    if (!dev_alloc(&ds, (size_t)n_seq) || !dev_alloc(&dl, (size_t)n_seq)) return LB2_ERR_CUDA;
     cudaMemcpy(ds, start.data(), n_seq * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(dn, node.data(), n_seq * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(doff, off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice);
-    const bool ok = launch_attention(0, (const __half*)dqkv, ds, dn, doff, 0, max_len, n_seq, hidden, heads, (__half*)dctx);
+    cudaMemcpy(dl, h_seq_len, n_seq * 4, cudaMemcpyHostToDevice);
+    const bool ok = launch_attention(0, (const __half*)dqkv, ds, dl, 0, max_len, n_seq, hidden, heads, (__half*)dctx);
     cudaError_t e = cudaDeviceSynchronize();
-    dev_free(&ds); dev_free(&dn); dev_free(&doff);
+    dev_free(&ds); dev_free(&dl);
     if (!ok) return LB2_ERR_CUDA;
     if (e != cudaSuccess) { set_error("attention: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     return LB2_OK;

@@ -63,13 +63,14 @@ struct Encoder {
     // workspaces, sized for `cap_tokens` packed tokens / `cap_seqs` sequences
     int64_t cap_tokens = 0, cap_seqs = 0;
     __half *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
+    int32_t* seq_len = nullptr;  // [cap_seqs] truncated passage lengths of the current pass
     int num_sms = 148;
 };
 
 size_t encoder_weight_floats(const EncoderConfig& cfg);
 bool encoder_load(Encoder* enc, const EncoderConfig& cfg, const float* host_weights, size_t n_floats);
 void encoder_free(Encoder* enc);
-bool encoder_reserve(Encoder* enc, int64_t tokens);
+bool encoder_reserve(Encoder* enc, int64_t tokens, int64_t seqs);
 // Encode n_seq passages.  Passage i is node seq_node[i] of the token store (tok_store / tok_off,
 // device pointers); its rows in the packed activation matrix start at seq_start[i] - row_base;
 // n_tokens = packed row count.  Writes pooled (+normalised) fp32 embeddings to out[n_seq, H].
@@ -78,15 +79,9 @@ bool encoder_forward(Encoder* enc, cudaStream_t stream, const uint16_t* tok_stor
                      float* out);
 
 // kernels exposed for the unit-test hooks in api.cu
-bool launch_embed_ln(cudaStream_t s, const Encoder* enc, const uint16_t* tok_store, const uint64_t* tok_off,
-                     const int32_t* seq_node, const int32_t* seq_start, int row_base, int n_seq, __half* x);
 bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const float* b, __half* out, int rows,
                       int hidden, float eps);
-bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_node,
-                      const uint64_t* tok_off, int row_base, int max_pos, int n_seq, int hidden, int heads,
-                      __half* ctx);
-bool launch_pool(cudaStream_t s, const __half* x, const int32_t* seq_start, const int32_t* seq_node,
-                 const uint64_t* tok_off, int row_base, int max_pos, int n_seq, int hidden, int pooling,
-                 int normalize, float* out);
+bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
+                      int max_pos, int n_seq, int hidden, int heads, __half* ctx);
 
 }  // namespace lb2

@@ -40,11 +40,12 @@ embed_ln_kernel(const uint16_t* __restrict__ tok_store, const uint64_t* __restri
                 const int32_t* __restrict__ seq_node, const int32_t* __restrict__ seq_start, int row_base,
                 int max_pos, const __half* __restrict__ word_emb, const __half* __restrict__ pos_emb,
                 const __half* __restrict__ type_emb, const float* __restrict__ g, const float* __restrict__ b,
-                float eps, __half* __restrict__ x) {
+                float eps, __half* __restrict__ x, int32_t* __restrict__ seq_len_out) {
     constexpr int H = VPL * 32;
     const int s = blockIdx.x;
     const int node = seq_node[s];
     const int len = passage_len(tok_off, node, max_pos);
+    if (threadIdx.x == 0) seq_len_out[s] = len;  // attention / pooling read the length from here
     const uint16_t* toks = tok_store + tok_off[node];
     const int row0 = seq_start[s] - row_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -164,129 +165,149 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One CTA = (sequence, head, block of 64 query rows); 4 warps x 16 rows.  Keys/values stream through a
+// double-buffered 64-key smem ring filled with cp.async (zero-fill past L), so the CTA's footprint is
+// 20 KB whatever the sequence length and several CTAs per SM overlap each other's load latency.
 template <int HD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq_start,
-                 const int32_t* __restrict__ seq_node, const uint64_t* __restrict__ tok_off, int row_base,
-                 int max_pos, int hidden, __half* __restrict__ ctx) {
-    extern __shared__ __align__(16) uint8_t att_smem[];
+                 const int32_t* __restrict__ seq_len, int row_base, int hidden, __half* __restrict__ ctx) {
+    constexpr int P = HD + 8;  // row pitch in halves: 16-byte aligned rows, conflict-free ldmatrix
+    __shared__ __align__(16) __half Ks[2][64 * P];
+    __shared__ __align__(16) __half Vs[2][64 * P];
     const int s = blockIdx.x, h = blockIdx.y;
-    const int L = passage_len(tok_off, seq_node[s], max_pos);
+    const int L = seq_len[s];
+    const int qblk0 = blockIdx.z * 64;
+    if (qblk0 >= L) return;
     const int row0 = seq_start[s] - row_base;
     const int ld = 3 * hidden;
-    constexpr int P = HD + 8;               // row pitch in halves: 16-byte aligned rows, conflict-free ldmatrix
-    const int Lp = (L + 63) & ~63;          // keys padded to the 64-key block
-    __half* Ks = reinterpret_cast<__half*>(att_smem);  // [Lp][P]
-    __half* Vs = Ks + static_cast<size_t>(Lp) * P;     // [Lp][P]
     const __half* qbase = qkv + static_cast<size_t>(row0) * ld + h * HD;
     const __half* kbase = qbase + hidden;
     const __half* vbase = qbase + 2 * hidden;
+    const int nkb = (L + 63) >> 6;
 
-    // stage K and V row-major with 16-byte copies; padded keys are zero
-    for (int idx = threadIdx.x; idx < Lp * (HD / 8); idx += blockDim.x) {
-        const int key = idx / (HD / 8), c8 = (idx % (HD / 8)) * 8;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (key < L) {
-            kv = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(key) * ld + c8));
-            vv = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * ld + c8));
+    auto prefetch = [&](int kb, int buf) {
+        for (int idx = threadIdx.x; idx < 64 * (HD / 8); idx += 128) {
+            const int kl = idx / (HD / 8), c8 = (idx % (HD / 8)) * 8;
+            const int key = kb * 64 + kl;
+            const int ok = key < L ? 16 : 0;           // src-size 0 -> the 16 bytes are zero-filled
+            const size_t roff = static_cast<size_t>(key < L ? key : L - 1) * ld + c8;
+            cp_async16(&Ks[buf][kl * P + c8], kbase + roff, ok);
+            cp_async16(&Vs[buf][kl * P + c8], vbase + roff, ok);
         }
-        *reinterpret_cast<uint4*>(Ks + key * P + c8) = kv;
-        *reinterpret_cast<uint4*>(Vs + key * P + c8) = vv;
-    }
-    __syncthreads();
+        cp_async_commit();
+    };
+    prefetch(0, 0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const float scale_log2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
-    // ldmatrix row addressing: lanes 0-7 / 8-15 / 16-23 / 24-31 supply the rows of matrices 0..3
     const int lm_row = lane & 7, lm_mat = lane >> 3;
+    const int q0 = qblk0 + warp * 16;
+    const bool active = q0 < L;  // warp-uniform
+    const int r0 = q0 + g, r1 = q0 + g + 8;
 
-    for (int q0 = warp * 16; q0 < L; q0 += 64) {
-        // Q fragments (A operand), rows q0+g and q0+g+8, straight from global (64 B per row)
-        uint32_t qa[HD / 16][4];
-        const int r0 = q0 + g, r1 = q0 + g + 8;
+    // Q fragments (A operand) straight from global (64 B per row), in flight together with key block 0
+    uint32_t qa[HD / 16][4];
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ks++) {
-            const int c = ks * 16 + 2 * t;
-            qa[ks][0] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c)) : 0u;
-            qa[ks][1] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c)) : 0u;
-            qa[ks][2] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c + 8)) : 0u;
-            qa[ks][3] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c + 8)) : 0u;
-        }
-        float o[HD / 8][4];
+    for (int ks = 0; ks < HD / 16; ks++) {
+        const int c = ks * 16 + 2 * t;
+        qa[ks][0] = (active && r0 < L) ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c)) : 0u;
+        qa[ks][1] = (active && r1 < L) ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c)) : 0u;
+        qa[ks][2] = (active && r0 < L) ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r0) * ld + c + 8)) : 0u;
+        qa[ks][3] = (active && r1 < L) ? __ldg(reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r1) * ld + c + 8)) : 0u;
+    }
+    float o[HD / 8][4];
 #pragma unroll
-        for (int i = 0; i < HD / 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int i = 0; i < HD / 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-        for (int kb = 0; kb < Lp; kb += 64) {
-            // ---- S = Q K^T for 64 keys: B fragments of K^T are plain ldmatrix tiles of row-major K
-            float sc[8][4];
+    for (int kb = 0; kb < nkb; kb++) {
+        const int buf = kb & 1;
+        if (kb + 1 < nkb) { prefetch(kb + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        if (active) {
+            const __half* Kb = Ks[buf];
+            const __half* Vb = Vs[buf];
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++) {
-                sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            for (int hb = 0; hb < 2; hb++) {  // two halves of 32 keys keep the register footprint small
+                const int key0 = kb * 64 + hb * 32;
+                if (key0 >= L) break;  // wholly padded half (warp-uniform)
+                float sc[4][4];
 #pragma unroll
-                for (int kp = 0; kp < HD / 32; kp++) {  // one x4 = (b0,b1) of two consecutive k-steps
-                    uint32_t b[4];
-                    ldsm_x4(b, Ks + (kb + nt * 8 + lm_row) * P + kp * 32 + lm_mat * 8);
-                    mma_16816(sc[nt], qa[2 * kp], b[0], b[1]);
-                    mma_16816(sc[nt], qa[2 * kp + 1], b[2], b[3]);
+                for (int nt = 0; nt < 4; nt++) {
+                    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+                    for (int kp = 0; kp < HD / 32; kp++) {
+                        uint32_t b[4];
+                        ldsm_x4(b, Kb + (hb * 32 + nt * 8 + lm_row) * P + kp * 32 + lm_mat * 8);
+                        mma_16816(sc[nt], qa[2 * kp], b[0], b[1]);
+                        mma_16816(sc[nt], qa[2 * kp + 1], b[2], b[3]);
+                    }
+                }
+                float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const int key = key0 + nt * 8 + 2 * t;
+                    if (key >= L) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+                    if (key + 1 >= L) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
+                    bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+                    bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+                }
+                bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+                bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+                bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+                bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+                const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);  // finite: key0 < L is a valid key
+                const float corr0 = fast_exp2((m0 - nm0) * scale_log2), corr1 = fast_exp2((m1 - nm1) * scale_log2);
+                m0 = nm0; m1 = nm1;
+                const float ms0 = m0 * scale_log2, ms1 = m1 * scale_log2;
+                float rs0 = 0.f, rs1 = 0.f;
+                uint32_t pa[2][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) {
+                    const float p0 = fast_exp2(fmaf(sc[nt][0], scale_log2, -ms0)), p1 = fast_exp2(fmaf(sc[nt][1], scale_log2, -ms0));
+                    const float p2 = fast_exp2(fmaf(sc[nt][2], scale_log2, -ms1)), p3 = fast_exp2(fmaf(sc[nt][3], scale_log2, -ms1));
+                    rs0 += p0 + p1; rs1 += p2 + p3;
+                    const int kk = nt >> 1;
+                    if ((nt & 1) == 0) { pa[kk][0] = pack_h2(p0, p1); pa[kk][1] = pack_h2(p2, p3); }
+                    else               { pa[kk][2] = pack_h2(p0, p1); pa[kk][3] = pack_h2(p2, p3); }
+                }
+                l0 = l0 * corr0 + rs0; l1 = l1 * corr1 + rs1;
+#pragma unroll
+                for (int dt = 0; dt < HD / 8; dt++) { o[dt][0] *= corr0; o[dt][1] *= corr0; o[dt][2] *= corr1; o[dt][3] *= corr1; }
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+#pragma unroll
+                    for (int dp = 0; dp < HD / 16; dp++) {
+                        uint32_t b[4];
+                        ldsm_x4_trans(b, Vb + (hb * 32 + kk * 16 + (lm_mat & 1) * 8 + lm_row) * P + (2 * dp + (lm_mat >> 1)) * 8);
+                        mma_16816(o[2 * dp], pa[kk], b[0], b[1]);
+                        mma_16816(o[2 * dp + 1], pa[kk], b[2], b[3]);
+                    }
                 }
             }
-            // ---- mask padded keys, running max
-            float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) {
-                const int key = kb + nt * 8 + 2 * t;
-                if (key >= L) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
-                if (key + 1 >= L) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
-                bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
-                bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
-            }
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-            const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);  // finite: every block holds a valid key
-            const float corr0 = fast_exp2((m0 - nm0) * scale_log2), corr1 = fast_exp2((m1 - nm1) * scale_log2);
-            m0 = nm0; m1 = nm1;
-            const float ms0 = m0 * scale_log2, ms1 = m1 * scale_log2;
-            float rs0 = 0.f, rs1 = 0.f;
-            uint32_t pa[4][4];
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) {
-                const float p0 = fast_exp2(fmaf(sc[nt][0], scale_log2, -ms0)), p1 = fast_exp2(fmaf(sc[nt][1], scale_log2, -ms0));
-                const float p2 = fast_exp2(fmaf(sc[nt][2], scale_log2, -ms1)), p3 = fast_exp2(fmaf(sc[nt][3], scale_log2, -ms1));
-                rs0 += p0 + p1; rs1 += p2 + p3;
-                const int kk = nt >> 1;
-                if ((nt & 1) == 0) { pa[kk][0] = pack_h2(p0, p1); pa[kk][1] = pack_h2(p2, p3); }
-                else               { pa[kk][2] = pack_h2(p0, p1); pa[kk][3] = pack_h2(p2, p3); }
-            }
-            l0 = l0 * corr0 + rs0; l1 = l1 * corr1 + rs1;
-#pragma unroll
-            for (int dt = 0; dt < HD / 8; dt++) { o[dt][0] *= corr0; o[dt][1] *= corr0; o[dt][2] *= corr1; o[dt][3] *= corr1; }
-            // ---- O += P V: B fragments of row-major V come from transposed ldmatrix tiles
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {       // 16 keys per k-step
-#pragma unroll
-                for (int dp = 0; dp < HD / 16; dp++) {  // one x4.trans = (b0,b1) for two 8-wide d tiles
-                    uint32_t b[4];
-                    // matrices: 0 -> keys +0..7, d tile 2dp ; 1 -> keys +8..15, d tile 2dp ; 2,3 -> d tile 2dp+1
-                    ldsm_x4_trans(b, Vs + (kb + kk * 16 + (lm_mat & 1) * 8 + lm_row) * P + (2 * dp + (lm_mat >> 1)) * 8);
-                    mma_16816(o[2 * dp], pa[kk], b[0], b[1]);
-                    mma_16816(o[2 * dp + 1], pa[kk], b[2], b[3]);
-                }
-            }
         }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-        __half* c0 = ctx + static_cast<size_t>(row0 + r0) * hidden + h * HD + 2 * t;
-        __half* c1 = ctx + static_cast<size_t>(row0 + r1) * hidden + h * HD + 2 * t;
+        __syncthreads();  // everyone is done with `buf` before the next iteration's prefetch overwrites it
+    }
+    if (!active) return;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    __half* c0 = ctx + static_cast<size_t>(row0 + r0) * hidden + h * HD + 2 * t;
+    __half* c1 = ctx + static_cast<size_t>(row0 + r1) * hidden + h * HD + 2 * t;
 #pragma unroll
-        for (int dt = 0; dt < HD / 8; dt++) {
-            if (r0 < L) *reinterpret_cast<uint32_t*>(c0 + dt * 8) = pack_h2(o[dt][0] * inv0, o[dt][1] * inv0);
-            if (r1 < L) *reinterpret_cast<uint32_t*>(c1 + dt * 8) = pack_h2(o[dt][2] * inv1, o[dt][3] * inv1);
-        }
+    for (int dt = 0; dt < HD / 8; dt++) {
+        if (r0 < L) *reinterpret_cast<uint32_t*>(c0 + dt * 8) = pack_h2(o[dt][0] * inv0, o[dt][1] * inv0);
+        if (r1 < L) *reinterpret_cast<uint32_t*>(c1 + dt * 8) = pack_h2(o[dt][2] * inv1, o[dt][3] * inv1);
     }
 }
 
@@ -296,12 +317,11 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq
 template <int EPT>  // elements per thread = hidden / 128
 __global__ void __launch_bounds__(128)
 pool_kernel(const __half* __restrict__ x, const int32_t* __restrict__ seq_start,
-            const int32_t* __restrict__ seq_node, const uint64_t* __restrict__ tok_off, int row_base, int max_pos,
-            int pooling, int normalize, float* __restrict__ out) {
+            const int32_t* __restrict__ seq_len, int row_base, int pooling, int normalize, float* __restrict__ out) {
     constexpr int H = EPT * 128;
     __shared__ float red[4];
     const int s = blockIdx.x;
-    const int L = passage_len(tok_off, seq_node[s], max_pos);
+    const int L = seq_len[s];
     const __half* xp = x + static_cast<size_t>(seq_start[s] - row_base) * H;
     float acc[EPT];
 #pragma unroll
@@ -335,17 +355,18 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // launch wrappers
 // ---------------------------------------------------------------------------------------
 bool launch_embed_ln(cudaStream_t s, const Encoder* enc, const uint16_t* tok_store, const uint64_t* tok_off,
-                     const int32_t* seq_node, const int32_t* seq_start, int row_base, int n_seq, __half* x) {
+                     const int32_t* seq_node, const int32_t* seq_start, int row_base, int n_seq, __half* x,
+                     int32_t* seq_len_out) {
     if (n_seq <= 0) return true;
     const EncoderConfig& c = enc->cfg;
     if (c.hidden == 384)
         embed_ln_kernel<12><<<n_seq, 256, 0, s>>>(tok_store, tok_off, seq_node, seq_start, row_base, c.max_pos,
                                                    enc->word_emb, enc->pos_emb, enc->type_emb, enc->emb_ln_g,
-                                                   enc->emb_ln_b, c.ln_eps, x);
+                                                   enc->emb_ln_b, c.ln_eps, x, seq_len_out);
     else
         embed_ln_kernel<24><<<n_seq, 256, 0, s>>>(tok_store, tok_off, seq_node, seq_start, row_base, c.max_pos,
                                                    enc->word_emb, enc->pos_emb, enc->type_emb, enc->emb_ln_g,
-                                                   enc->emb_ln_b, c.ln_eps, x);
+                                                   enc->emb_ln_b, c.ln_eps, x, seq_len_out);
     LB2_CUDA_OK(cudaGetLastError());
     return true;
 }
@@ -366,23 +387,16 @@ bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const fl
     return true;
 }
 
-bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_node,
-                      const uint64_t* tok_off, int row_base, int max_pos, int n_seq, int hidden, int heads,
-                      __half* ctx) {
+bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
+                      int max_pos, int n_seq, int hidden, int heads, __half* ctx) {
     if (n_seq <= 0) return true;
     const int hd = hidden / heads;
-    const int Lp = (max_pos + 63) & ~63;
-    const size_t smem = 2 * static_cast<size_t>(Lp) * (hd + 8) * sizeof(__half);
-    dim3 grid(n_seq, heads);
-    if (hd == 32) {
-        static bool set32 = false;
-        if (!set32) { LB2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set32 = true; }
-        attention_kernel<32><<<grid, 128, smem, s>>>(qkv, seq_start, seq_node, tok_off, row_base, max_pos, hidden, ctx);
-    } else if (hd == 64) {
-        static bool set64 = false;
-        if (!set64) { LB2_CUDA_OK(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set64 = true; }
-        attention_kernel<64><<<grid, 128, smem, s>>>(qkv, seq_start, seq_node, tok_off, row_base, max_pos, hidden, ctx);
-    } else {
+    dim3 grid(n_seq, heads, (max_pos + 63) / 64);
+    if (hd == 32)
+        attention_kernel<32><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, hidden, ctx);
+    else if (hd == 64)
+        attention_kernel<64><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, hidden, ctx);
+    else {
         set_error("attention: unsupported head_dim %d", hd);
         return false;
     }
@@ -390,14 +404,13 @@ bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_star
     return true;
 }
 
-bool launch_pool(cudaStream_t s, const __half* x, const int32_t* seq_start, const int32_t* seq_node,
-                 const uint64_t* tok_off, int row_base, int max_pos, int n_seq, int hidden, int pooling,
-                 int normalize, float* out) {
+bool launch_pool(cudaStream_t s, const __half* x, const int32_t* seq_start, const int32_t* seq_len, int row_base,
+                 int n_seq, int hidden, int pooling, int normalize, float* out) {
     if (n_seq <= 0) return true;
     if (hidden == 384)
-        pool_kernel<3><<<n_seq, 128, 0, s>>>(x, seq_start, seq_node, tok_off, row_base, max_pos, pooling, normalize, out);
+        pool_kernel<3><<<n_seq, 128, 0, s>>>(x, seq_start, seq_len, row_base, pooling, normalize, out);
     else if (hidden == 768)
-        pool_kernel<6><<<n_seq, 128, 0, s>>>(x, seq_start, seq_node, tok_off, row_base, max_pos, pooling, normalize, out);
+        pool_kernel<6><<<n_seq, 128, 0, s>>>(x, seq_start, seq_len, row_base, pooling, normalize, out);
     else {
         set_error("pool: unsupported hidden %d", hidden);
         return false;
@@ -510,11 +523,20 @@ void encoder_free(Encoder* enc) {
         if (*p) cudaFree(*p);
         *p = nullptr;
     }
+    if (enc->seq_len) cudaFree(enc->seq_len);
+    enc->seq_len = nullptr;
     enc->cap_tokens = enc->cap_seqs = 0;
     enc->loaded = false;
 }
 
-bool encoder_reserve(Encoder* enc, int64_t tokens) {
+bool encoder_reserve(Encoder* enc, int64_t tokens, int64_t seqs) {
+    if (seqs > enc->cap_seqs) {
+        if (enc->seq_len) cudaFree(enc->seq_len);
+        enc->seq_len = nullptr;
+        enc->cap_seqs = 0;
+        LB2_CUDA_OK(cudaMalloc(&enc->seq_len, static_cast<size_t>(seqs) * sizeof(int32_t)));
+        enc->cap_seqs = seqs;
+    }
     if (tokens <= enc->cap_tokens) return true;
     for (__half** p : {&enc->x, &enc->y, &enc->qkv, &enc->ctx, &enc->ffn}) {
         if (*p) cudaFree(*p);
@@ -536,10 +558,14 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
                      float* out) {
     if (!enc->loaded) { set_error("encoder not loaded"); return false; }
     if (n_seq <= 0 || n_tokens <= 0) return true;
-    if (n_tokens > enc->cap_tokens) { set_error("encoder_forward: %d tokens exceed the reserved %lld", n_tokens, (long long)enc->cap_tokens); return false; }
+    if (n_tokens > enc->cap_tokens || n_seq > enc->cap_seqs) {
+        set_error("encoder_forward: %d tokens / %d passages exceed the reserved %lld / %lld", n_tokens, n_seq,
+                  (long long)enc->cap_tokens, (long long)enc->cap_seqs);
+        return false;
+    }
     const EncoderConfig& c = enc->cfg;
     const int H = c.hidden, F = c.ffn, T = n_tokens, sms = enc->num_sms;
-    if (!launch_embed_ln(st, enc, tok_store, tok_off, seq_node, seq_start, row_base, n_seq, enc->x)) return false;
+    if (!launch_embed_ln(st, enc, tok_store, tok_off, seq_node, seq_start, row_base, n_seq, enc->x, enc->seq_len)) return false;
     auto gemm = [&](const __half* A, const CUtensorMap* tm, const __half* W, const float* bias, const __half* res,
                     __half* C, int N, int K, int epi) {
         gemm_profile_begin(st);
@@ -550,14 +576,14 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
     for (int l = 0; l < c.layers; l++) {
         const LayerWeights& w = enc->layers[l];
         if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS)) return false;
-        if (!launch_attention(st, enc->qkv, seq_start, seq_node, tok_off, row_base, c.max_pos, n_seq, H, c.heads, enc->ctx)) return false;
+        if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, row_base, c.max_pos, n_seq, H, c.heads, enc->ctx)) return false;
         if (!gemm(enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, enc->y, H, H, EPI_BIAS_RES)) return false;
         if (!launch_layernorm(st, enc->y, w.ln1_g, w.ln1_b, enc->x, T, H, c.ln_eps)) return false;
         if (!gemm(enc->x, &w.tm_1, w.w_1, w.b_1, nullptr, enc->ffn, F, H, EPI_BIAS_GELU)) return false;
         if (!gemm(enc->ffn, &w.tm_2, w.w_2, w.b_2, enc->x, enc->y, H, F, EPI_BIAS_RES)) return false;
         if (!launch_layernorm(st, enc->y, w.ln2_g, w.ln2_b, enc->x, T, H, c.ln_eps)) return false;
     }
-    return launch_pool(st, enc->x, seq_start, seq_node, tok_off, row_base, c.max_pos, n_seq, H, c.pooling, c.normalize, out);
+    return launch_pool(st, enc->x, seq_start, enc->seq_len, row_base, n_seq, H, c.pooling, c.normalize, out);
 }
 
 }  // namespace lb2
