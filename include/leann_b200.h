@@ -145,9 +145,9 @@ int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const 
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);
 int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden,
                            float eps);
-/* qkv: packed [sum(len), 3*hidden] fp16 on the device; h_seq_len: HOST int32[n_seq] */
-int lb2_test_attention_f16(const void* dqkv, const int32_t* h_seq_len, int n_seq, int hidden, int heads,
-                           int max_len, void* dctx);
+/* qkv: packed [sum(len), 3*hidden] fp16; d_seq_start / d_seq_len: device int32[n_seq] (first row, length) */
+int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq,
+                           int hidden, int heads, int max_len, void* dctx);
 
 #ifdef __cplusplus
 }

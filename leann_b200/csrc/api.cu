@@ -662,18 +662,10 @@ int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, vo
     return LB2_OK;
 }
 
-int lb2_test_attention_f16(const void* dqkv, const int32_t* h_seq_len, int n_seq, int hidden, int heads, int max_len,
-                           void* dctx) {
-    std::vector<int> start((size_t)n_seq);
-    int acc = 0;
-    for (int i = 0; i < n_seq; i++) { start[i] = acc; acc += h_seq_len[i]; }
-    int *ds = nullptr, *dl = nullptr;
-    if (!dev_alloc(&ds, (size_t)n_seq) || !dev_alloc(&dl, (size_t)n_seq)) return LB2_ERR_CUDA;
-    cudaMemcpy(ds, start.data(), n_seq * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(dl, h_seq_len, n_seq * 4, cudaMemcpyHostToDevice);
-    const bool ok = launch_attention(0, (const __half*)dqkv, ds, dl, 0, max_len, n_seq, hidden, heads, (__half*)dctx);
+int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq, int hidden,
+                           int heads, int max_len, void* dctx) {
+    const bool ok = launch_attention(0, (const __half*)dqkv, d_seq_start, d_seq_len, 0, max_len, n_seq, hidden, heads, (__half*)dctx);
     cudaError_t e = cudaDeviceSynchronize();
-    dev_free(&ds); dev_free(&dl);
     if (!ok) return LB2_ERR_CUDA;
     if (e != cudaSuccess) { set_error("attention: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     return LB2_OK;

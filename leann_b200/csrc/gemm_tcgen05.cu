@@ -267,202 +267,6 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// Weight-stationary variant for the K = 384 layers without residual (QKV, FFN-up).
-// The streaming kernel above re-reads its 192 x K weight tile from L2 for every M tile, and at
-// 128x192 tiles the L2 -> SM path (not the tensor pipe) is what saturates (~77 flop per L2 byte).
-// Here each CTA owns ONE 192-row slice of W for its whole life: the slice (K/64 swizzled k-blocks,
-// 144 KB for K = 384) is loaded once and stays in shared memory; only the A tiles stream through a
-// 3-stage ring.  L2 traffic per tile drops from (128+192)*K to 128*K halves.
-// ---------------------------------------------------------------------------------------
-template <int BLOCK_N, int KBLOCKS, int STAGES>
-struct GemmWsSmem {
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int WK_BYTES = BLOCK_N * BLOCK_K * 2;  // one k-block of the resident slice
-    static constexpr int W_BYTES = KBLOCKS * WK_BYTES;
-    static constexpr int A_OFFSET = W_BYTES;
-    static constexpr int EPI_BOXES = 2;  // rotating 32x32 boxes per epilogue warp
-    static constexpr int EPI_OFFSET = A_OFFSET + STAGES * A_BYTES;
-    static constexpr int EPI_BYTES = EPI_WARPS * EPI_BOXES * 2048;
-    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 5) * 8 + 16 + 1024;
-};
-
-template <int BLOCK_N, int KBLOCKS, int STAGES, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, int M, int N) {
-    using L = GemmWsSmem<BLOCK_N, KBLOCKS, STAGES>;
-    static_assert(EPI != EPI_BIAS_RES, "residual layers use the streaming kernel");
-    constexpr int TMEM_COLS = 512;
-    static_assert(2 * BLOCK_N <= 512 && BLOCK_N % 64 == 0, "accumulator stages");
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* w_bar = tmem_empty + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
-    const int num_n = N / BLOCK_N;
-    const int n_blk = blockIdx.x % num_n;        // this CTA's weight slice
-    const int m_first = blockIdx.x / num_n;
-    const int m_step = gridDim.x / num_n;        // gridDim.x is a multiple of num_n
-
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&tmap_a);
-        ptx::prefetch_tmap(&tmap_b);
-        ptx::prefetch_tmap(&tmap_c);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; i++) {
-            ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
-        }
-        for (int i = 0; i < 2; i++) {
-            ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], EPI_WARPS);
-        }
-        ptx::mbar_init(w_bar, 1);
-        ptx::fence_barrier_init();
-    }
-    if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer: resident weight slice once, then the A tiles =====
-            ptx::mbar_expect_tx(w_bar, L::W_BYTES);
-            for (int kb = 0; kb < KBLOCKS; kb++)
-                ptx::tma_load_2d(smem + kb * L::WK_BYTES, &tmap_b, w_bar, kb * BLOCK_K, n_blk * BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int m_blk = m_first; m_blk < num_m; m_blk += m_step) {
-                for (int kb = 0; kb < KBLOCKS; kb++) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&full_bar[stage], L::A_BYTES);
-                    ptx::tma_load_2d(smem + L::A_OFFSET + stage * L::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K,
-                                     m_blk * BLOCK_M);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
-            ptx::mbar_wait(w_bar, 0);
-            ptx::tc_fence_after();
-            const uint32_t w_base = ptx::smem_u32(smem);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int m_blk = m_first; m_blk < num_m; m_blk += m_step, it++) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < KBLOCKS; kb++) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::A_OFFSET + stage * L::A_BYTES));
-                    const uint64_t b_desc = ptx::make_sw128_kmajor_desc(w_base + kb * L::WK_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; k++)
-                        ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-                ptx::umma_commit(&tmem_full[as]);
-            }
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue (same scheme as the streaming kernel, two rotating smem boxes per warp) =====
-        const int quarter = warp & 3;
-        const int ew = warp - 4;
-        const int half = ew >> 2;
-        constexpr int NCH = BLOCK_N / 32 / 2;
-        uint8_t* stage_buf = smem + L::EPI_OFFSET + ew * L::EPI_BOXES * 2048;
-        const int swz = (lane >> 1) & 3;
-        int box_i = 0;
-        int it = 0;
-        for (int m_blk = m_first; m_blk < num_m; m_blk += m_step, it++) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int row0 = m_blk * BLOCK_M + quarter * 32;
-            const int colbase = n_blk * BLOCK_N + half * NCH * 32;
-            ptx::mbar_wait(&tmem_full[as], aphase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + half * NCH * 32;
-            uint32_t r[2][32];
-            ptx::tmem_ld_32x32(taddr, r[0]);
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                ptx::tmem_ld_wait();
-                if (c + 1 < NCH) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-                const uint32_t(&acc)[32] = r[c & 1];
-                const int col0 = colbase + c * 32;
-                uint8_t* boxbase = stage_buf + box_i * 2048;
-                uint8_t* box = boxbase + lane * 64;
-                if (lane == 0) ptx::bulk_wait_read<L::EPI_BOXES - 1>();  // the store that last used this box is done reading
-                __syncwarp();
-                const float4* bp = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; j4++) {
-                    float v[8];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const float4 b4 = __ldg(bp + 2 * j4 + u);
-                        v[4 * u + 0] = __uint_as_float(acc[8 * j4 + 4 * u + 0]) + b4.x;
-                        v[4 * u + 1] = __uint_as_float(acc[8 * j4 + 4 * u + 1]) + b4.y;
-                        v[4 * u + 2] = __uint_as_float(acc[8 * j4 + 4 * u + 2]) + b4.z;
-                        v[4 * u + 3] = __uint_as_float(acc[8 * j4 + 4 * u + 3]) + b4.w;
-                    }
-                    if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-                        for (int u = 0; u < 8; u++) v[u] = gelu_fast(v[u]);
-                    }
-                    uint4 ov;
-                    __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
-                    *reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4)) = ov;
-                }
-                ptx::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    ptx::tma_store_2d(&tmap_c, boxbase, col0, row0);
-                    ptx::bulk_commit();
-                }
-                box_i ^= 1;
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
-        }
-        if (lane == 0) ptx::bulk_wait_all();
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -526,28 +330,6 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     return cudaGetLastError();
 }
 
-constexpr int WS_KBLOCKS = 6;  // K = 384
-constexpr int WS_STAGES = 3;
-
-template <int EPI>
-static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                                  const float* bias, int M, int N, int num_sms) {
-    using L = GemmWsSmem<GEMM_BLOCK_N, WS_KBLOCKS, WS_STAGES>;
-    auto kern = gemm_f16_ws_kernel<GEMM_BLOCK_N, WS_KBLOCKS, WS_STAGES, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    const int num_n = N / GEMM_BLOCK_N;
-    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
-    int per_slice = num_sms / num_n;
-    if (per_slice > num_m) per_slice = num_m;
-    kern<<<per_slice * num_n, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N);
-    return cudaGetLastError();
-}
-
 // A [M,K] fp16 row-major, W [N,K] fp16 row-major (nn.Linear layout), C [M,N] fp16.
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms) {
@@ -569,18 +351,6 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
         tmap_w = &tb_local;
     }
     cudaError_t e;
-    const int ws_slices = N / GEMM_BLOCK_N;
-    const bool use_ws = K == WS_KBLOCKS * BLOCK_K && epi != EPI_BIAS_RES && ws_slices <= num_sms &&
-                        (M + BLOCK_M - 1) / BLOCK_M >= 2 * (num_sms / ws_slices);  // enough M tiles to amortise the slice load
-    if (use_ws) {
-        e = epi == EPI_BIAS ? launch_gemm_ws<EPI_BIAS>(stream, ta, *tmap_w, tc, bias, M, N, num_sms)
-                            : launch_gemm_ws<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, bias, M, N, num_sms);
-        if (e != cudaSuccess) {
-            set_error("gemm_f16 (weight-stationary) launch: %s", cudaGetErrorString(e));
-            return false;
-        }
-        return true;
-    }
     switch (epi) {
         case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
         case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;

@@ -65,8 +65,9 @@ def test_attention_vs_torch(lib, cuda_ok, H, heads):
     g = torch.Generator(device="cuda").manual_seed(H)
     qkv = (torch.randn(T, 3 * H, device="cuda", generator=g) * 1.5).half()
     ctx = torch.full((T, H), float("nan"), device="cuda", dtype=torch.float16)
-    hl = np.asarray(lens, np.int32)
-    rc = lib.lb2_test_attention_f16(qkv.data_ptr(), hl.ctypes.data, len(lens), H, heads, 256, ctx.data_ptr())
+    dl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    ds = (torch.cumsum(dl, 0) - dl).to(torch.int32)
+    rc = lib.lb2_test_attention_f16(qkv.data_ptr(), ds.data_ptr(), dl.data_ptr(), len(lens), H, heads, 256, ctx.data_ptr())
     assert rc == 0, lib.lb2_last_error()
     assert torch.isfinite(ctx).all()
     off = 0
