@@ -190,7 +190,7 @@ def run_b200(args):
     barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = dict(gpu_ms=0.0, encoder_ms=0.0, gemm_ms=0.0, gemm_flops=0.0, launches=0, ndis=0, nhops=0, n_recomputed=0,
+    agg = dict(gpu_ms=0.0, encoder_ms=0.0, gemm_ms=0.0, gemm_flops=0.0, attention_ms=0.0, norm_ms=0.0, launches=0, ndis=0, nhops=0, n_recomputed=0,
                n_requested=0, n_tokens=0, steps=0)
     recalls = []
     t_dev = 0.0
@@ -205,7 +205,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         t_dev += ev0.elapsed_time(ev1) / 1e3
         st = idx.last_stats
-        for key in ("gpu_ms", "encoder_ms", "gemm_ms", "gemm_flops", "ndis", "nhops", "n_recomputed", "n_requested", "n_tokens"):
+        for key in ("gpu_ms", "encoder_ms", "gemm_ms", "gemm_flops", "attention_ms", "norm_ms", "ndis", "nhops", "n_recomputed", "n_requested", "n_tokens"):
             agg[key] += getattr(st, key)
         agg["launches"] += st.n_kernel_launches
         agg["steps"] += st.n_steps
@@ -280,6 +280,8 @@ def run_b200(args):
                        "tokens_per_query": agg["n_tokens"] / (nq * args.steps),
                        "traversal_steps_per_call": agg["steps"] / args.steps,
                        "encoder_share": agg["encoder_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None,
+                       "attention_share": agg["attention_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None,
+                       "layernorm_share": agg["norm_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None,
                        "encoder_algorithmic_tflops": (agg["n_tokens"] * 0 + _encoder_flops(W, agg)) / (agg["encoder_ms"] / 1e3) / 1e12 if agg["encoder_ms"] else None,
                        "corpus_embed_tflops": W["embed_tflops"]},
         }

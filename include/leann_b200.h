@@ -69,6 +69,8 @@ typedef struct {
     double encoder_ms;       /* of which recompute stage                                           */
     double gemm_ms;          /* of which tcgen05 GEMMs (only when LB2_PROFILE_GEMM=1)               */
     double gemm_flops;       /* algorithmic flops of those GEMMs                                    */
+    double attention_ms;     /* attention kernels (profiling on)                                    */
+    double norm_ms;          /* LayerNorm kernels (profiling on)                                    */
 } lb2_search_stats;
 
 typedef struct {

@@ -32,7 +32,7 @@ class SearchStats(C.Structure):
     _fields_ = [("ndis", C.c_int64), ("nhops", C.c_int64), ("n_recomputed", C.c_int64), ("n_requested", C.c_int64),
                 ("n_tokens", C.c_int64), ("n_steps", C.c_int64), ("n_kernel_launches", C.c_int64),
                 ("gpu_ms", C.c_double), ("encoder_ms", C.c_double), ("gemm_ms", C.c_double),
-                ("gemm_flops", C.c_double)]
+                ("gemm_flops", C.c_double), ("attention_ms", C.c_double), ("norm_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

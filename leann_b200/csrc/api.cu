@@ -156,18 +156,17 @@ struct lb2_index {
 };
 
 namespace lb2 {
-// encoder.cu consults this to time its GEMM launches when profiling is on
-EventPool* g_gemm_events = nullptr;
+// encoder.cu calls these around its launches; they record CUDA events only when profiling is on
+static EventPool g_prof_pool[PROF_NCAT];
+static bool g_prof_on = false;
 double g_gemm_flops = 0;
-void gemm_profile_begin(cudaStream_t s) { if (g_gemm_events) cudaEventRecord(g_gemm_events->get(), s); }
-void gemm_profile_end(cudaStream_t s, double flops) {
-    if (g_gemm_events) { cudaEventRecord(g_gemm_events->get(), s); g_gemm_flops += flops; }
+void prof_begin(cudaStream_t s, int cat) { if (g_prof_on) cudaEventRecord(g_prof_pool[cat].get(), s); }
+void prof_end(cudaStream_t s, int cat, double flops) {
+    if (g_prof_on) { cudaEventRecord(g_prof_pool[cat].get(), s); if (cat == PROF_GEMM) g_gemm_flops += flops; }
 }
 }  // namespace lb2
 
 namespace {
-
-EventPool g_gemm_pool;
 
 bool use_device(const lb2_index* idx) {
     cudaError_t e = cudaSetDevice(idx->device);
@@ -318,8 +317,9 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     s.vectors = x->d_vectors; s.E = x->d_E; s.tok_off = x->d_tok_off; s.max_pos = x->enc.cfg.max_pos;
 
     x->ev_total.total_ms = 0; x->ev_enc.total_ms = 0;
-    g_gemm_pool.total_ms = 0; g_gemm_flops = 0;
-    g_gemm_events = x->profile_gemm ? &g_gemm_pool : nullptr;
+    for (auto& pl : g_prof_pool) pl.total_ms = 0;
+    g_gemm_flops = 0;
+    g_prof_on = x->profile_gemm;
     cudaEventRecord(x->ev_total.get(), st);
     if (!launch_init_slots(st, s)) return LB2_ERR_CUDA;
     long long launches = 1, steps = 0, n_recomputed = 0, n_tokens = 0;
@@ -355,21 +355,22 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
                 launches += encoder_kernels_per_pass(x->enc);
             }
             cudaEventRecord(x->ev_enc.get(), st);
-            if (x->ev_enc.used > 4000 || g_gemm_pool.used > 8000) {
+            if (x->ev_enc.used > 4000 || g_prof_pool[PROF_GEMM].used > 8000) {
                 cudaStreamSynchronize(st);
                 x->ev_enc.drain();
-                g_gemm_pool.drain();
+                for (auto& pl : g_prof_pool) pl.drain();
             }
         }
     }
     cudaEventRecord(x->ev_total.get(), st);
     cudaError_t e = cudaStreamSynchronize(st);
-    g_gemm_events = nullptr;
+    g_prof_on = false;
     if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     int done = 0;
     cudaMemcpy(&done, s.n_done, sizeof(int), cudaMemcpyDeviceToHost);
     if (done != nq) { set_error("internal: %d of %lld queries finished", done, (long long)nq); return LB2_ERR_CUDA; }
-    x->ev_total.drain(); x->ev_enc.drain(); g_gemm_pool.drain();
+    x->ev_total.drain(); x->ev_enc.drain();
+    for (auto& pl : g_prof_pool) pl.drain();
     if (stats) {
         std::vector<long long> a((size_t)nq), b((size_t)nq);
         cudaMemcpy(a.data(), x->d_qndis, nq * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -382,8 +383,10 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
         stats->n_kernel_launches = launches;
         stats->gpu_ms = x->ev_total.total_ms;
         stats->encoder_ms = x->ev_enc.total_ms;
-        stats->gemm_ms = g_gemm_pool.total_ms;
+        stats->gemm_ms = g_prof_pool[PROF_GEMM].total_ms;
         stats->gemm_flops = g_gemm_flops;
+        stats->attention_ms = g_prof_pool[PROF_ATTN].total_ms;
+        stats->norm_ms = g_prof_pool[PROF_NORM].total_ms;
     }
     return LB2_OK;
 }

@@ -27,9 +27,11 @@ bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms);
 int gemm_block_n();
-// optional per-GEMM timing (api.cu owns the event pool; no-ops unless profiling is on)
-void gemm_profile_begin(cudaStream_t s);
-void gemm_profile_end(cudaStream_t s, double flops);
+// optional per-kernel-class timing with CUDA events (api.cu owns the pools; no-ops unless
+// LB2_PROFILE_GEMM=1): category 0 = tcgen05 GEMMs, 1 = attention, 2 = LayerNorm / embed / pool
+enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_NORM = 2, PROF_NCAT = 3 };
+void prof_begin(cudaStream_t s, int cat);
+void prof_end(cudaStream_t s, int cat, double flops);
 
 // ---- encoder.cu
 struct EncoderConfig {

@@ -568,20 +568,26 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
     if (!launch_embed_ln(st, enc, tok_store, tok_off, seq_node, seq_start, row_base, n_seq, enc->x, enc->seq_len)) return false;
     auto gemm = [&](const __half* A, const CUtensorMap* tm, const __half* W, const float* bias, const __half* res,
                     __half* C, int N, int K, int epi) {
-        gemm_profile_begin(st);
+        prof_begin(st, PROF_GEMM);
         const bool ok = gemm_f16(st, A, tm, W, bias, res, C, T, N, K, epi, sms);
-        gemm_profile_end(st, 2.0 * T * (double)N * K);
+        prof_end(st, PROF_GEMM, 2.0 * T * (double)N * K);
         return ok;
     };
     for (int l = 0; l < c.layers; l++) {
         const LayerWeights& w = enc->layers[l];
         if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS)) return false;
+        prof_begin(st, PROF_ATTN);
         if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, row_base, c.max_pos, n_seq, H, c.heads, enc->ctx)) return false;
+        prof_end(st, PROF_ATTN, 0);
         if (!gemm(enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, enc->y, H, H, EPI_BIAS_RES)) return false;
+        prof_begin(st, PROF_NORM);
         if (!launch_layernorm(st, enc->y, w.ln1_g, w.ln1_b, enc->x, T, H, c.ln_eps)) return false;
+        prof_end(st, PROF_NORM, 0);
         if (!gemm(enc->x, &w.tm_1, w.w_1, w.b_1, nullptr, enc->ffn, F, H, EPI_BIAS_GELU)) return false;
         if (!gemm(enc->ffn, &w.tm_2, w.w_2, w.b_2, enc->x, enc->y, H, F, EPI_BIAS_RES)) return false;
+        prof_begin(st, PROF_NORM);
         if (!launch_layernorm(st, enc->y, w.ln2_g, w.ln2_b, enc->x, T, H, c.ln_eps)) return false;
+        prof_end(st, PROF_NORM, 0);
     }
     return launch_pool(st, enc->x, seq_start, enc->seq_len, row_base, n_seq, H, c.pooling, c.normalize, out);
 }
