@@ -57,7 +57,7 @@ def _knn(xq: torch.Tensor, xb: torch.Tensor, k: int, metric_ip: bool, self_pos: 
 
 @torch.no_grad()
 def _heuristic_prune(x: torch.Tensor, cand: torch.Tensor, cdist: torch.Tensor, keep: int, metric_ip: bool,
-                     fill: bool, block: int = 8192) -> torch.Tensor:
+                     fill: bool, alpha: float = 1.0, block: int = 8192) -> torch.Tensor:
     """HNSW neighbour selection over candidates sorted by distance (padding = -1 / +inf at the end);
     returns idx [n, keep] padded with -1.  fill=True tops the list up with the nearest pruned candidates."""
     n, K = cand.shape
@@ -73,6 +73,12 @@ def _heuristic_prune(x: torch.Tensor, cand: torch.Tensor, cdist: torch.Tensor, k
         ip = torch.bmm(cv, cv.transpose(1, 2)).float()
         pd = -ip if metric_ip else (sq[c][:, :, None] + sq[c][:, None, :] - 2 * ip)  # dist(c_i, c_j)
         dn = cdist[b0:b1]  # dist(node, c_j)
+        if alpha != 1.0:
+            # Vamana-style slack: a kept neighbour dominates c_j only if it is alpha times closer.  Needs a
+            # non-negative distance: for inner product use 2 - 2 ip (exact for unit vectors).
+            if metric_ip:
+                pd, dn = 2 + 2 * pd, 2 + 2 * dn
+            pd = pd * alpha
         kept = torch.zeros((b1 - b0, K), dtype=torch.bool, device=x.device)
         nk = torch.zeros(b1 - b0, dtype=torch.int64, device=x.device)
         for j in range(K):
@@ -130,7 +136,8 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
 
 @torch.no_grad()
 def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
-                     knn_factor: float = 1.5, n_scales: int = 2, verbose: bool = False) -> CSRGraph:
+                     knn_factor: float = 1.5, n_scales: int = 2, alpha: float = 1.0, union_factor: int = 2,
+                     verbose: bool = False) -> CSRGraph:
     metric_ip = metric.lower() in ("mips", "cosine", "ip")
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
     x = emb if isinstance(emb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(emb, np.float32))
@@ -175,9 +182,9 @@ def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, 
             cd = torch.where(dup, torch.full_like(cd, float("inf")), cd)
             o = torch.argsort(cd, dim=1, stable=True)
             ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
-            fwd = _heuristic_prune(xm, ci, cd, cap, metric_ip, fill=False)
-            ui, ud = _add_reverse_and_cap(xm, fwd, 2 * cap, metric_ip)
-            both = _heuristic_prune(xm, ui, ud, cap, metric_ip, fill=True)
+            fwd = _heuristic_prune(xm, ci, cd, cap, metric_ip, fill=False, alpha=alpha)
+            ui, ud = _add_reverse_and_cap(xm, fwd, union_factor * cap, metric_ip)
+            both = _heuristic_prune(xm, ui, ud, cap, metric_ip, fill=True, alpha=alpha)
             gl = torch.where(both >= 0, mt[both.clamp(min=0)], torch.full_like(both, -1))
             nb = gl.cpu().numpy().astype(np.int32)
         if l == 0:

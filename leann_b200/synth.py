@@ -164,7 +164,8 @@ class TopicModel:
         self.zipf_cdf[-1] = 1.0
         self.zipf_perm = rng.permutation(nwords).astype(np.int32) + FIRST_WORD_ID
 
-    def sample(self, n: int, seed: int, len_mean: float, len_std: float, len_min: int, len_max: int) -> Corpus:
+    def sample(self, n: int, seed: int, len_mean: float, len_std: float, len_min: int, len_max: int,
+               p_topic: float = 0.70, p_super: float = 0.15) -> Corpus:
         rng = np.random.default_rng(seed)
         topics = rng.integers(0, self.n_topics, n).astype(np.int32)
         lens = np.clip(np.rint(rng.normal(len_mean, len_std, n)), len_min, len_max).astype(np.int64)
@@ -174,8 +175,8 @@ class TopicModel:
         tok_topic = np.repeat(topics, lens)
         u = rng.random(total)
         src = rng.random(total)
-        m_topic, m_super = src < 0.70, (src >= 0.70) & (src < 0.85)
-        m_bg = src >= 0.85
+        m_topic, m_super = src < p_topic, (src >= p_topic) & (src < p_topic + p_super)
+        m_bg = src >= p_topic + p_super
         tokens = np.empty(total, np.uint16)
         tt = tok_topic[m_topic]
         idx = _searchsorted_right(self.flat_cdf, u[m_topic] + tt)  # one search over the concatenated CDFs
@@ -191,11 +192,13 @@ class TopicModel:
         return Corpus(tokens, offsets, topics)
 
 
-def make_corpus(n: int, vocab_size: int = 30522, seed: int = 1234, max_len: int = 256, n_topics: int | None = None):
+def make_corpus(n: int, vocab_size: int = 30522, seed: int = 1234, max_len: int = 256, n_topics: int | None = None,
+                p_topic: float = 0.70, p_super: float = 0.15):
     tm = TopicModel(vocab_size, n_topics or max(4, n // 32), seed)
-    corpus = tm.sample(n, seed + 1, 128, 48, 16, max_len)
+    corpus = tm.sample(n, seed + 1, 128, 48, 16, max_len, p_topic, p_super)
     return tm, corpus
 
 
-def make_queries(tm: TopicModel, nq: int, seed: int = 4321) -> Corpus:
-    return tm.sample(nq, seed, 24, 8, 4, 64)
+def make_queries(tm: TopicModel, nq: int, seed: int = 4321, len_mean: float = 24, p_topic: float = 0.70,
+                 p_super: float = 0.15) -> Corpus:
+    return tm.sample(nq, seed, len_mean, len_mean / 3, 4, 64, p_topic, p_super)
