@@ -114,10 +114,11 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
     key = torch.unique(a * n + b)
     a, b = key // n, key % n
     xs = x.half() if x.is_cuda else x
-    if metric_ip:
-        d = -(xs[a].float() * xs[b].float()).sum(1)
-    else:
-        d = ((xs[a].float() - xs[b].float()) ** 2).sum(1)
+    d = torch.empty(a.numel(), dtype=torch.float32, device=dev)
+    step = 1 << 22  # edge chunks: the gathered [chunk, dim] operands stay small
+    for e0 in range(0, a.numel(), step):
+        xa, xb = xs[a[e0:e0 + step]].float(), xs[b[e0:e0 + step]].float()
+        d[e0:e0 + step] = -(xa * xb).sum(1) if metric_ip else ((xa - xb) ** 2).sum(1)
     # sort by (a, d): stable two-pass
     o = torch.argsort(d, stable=True)
     a, b, d = a[o], b[o], d[o]
