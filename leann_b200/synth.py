@@ -133,8 +133,10 @@ class TopicModel:
 
     S super-topics own a private sub-vocabulary of `sub_vocab` words; each of the T topics belongs to
     one super-topic and is a peaked distribution over `topic_words` words drawn from it.  A passage
-    picks a topic and draws tokens 70 % from the topic, 15 % uniformly from the super-topic vocabulary,
-    15 % from a global Zipf background.  With ~32 passages per topic the exact top-10 of a query are
+    picks a topic and draws tokens 80 % from the topic, 10 % uniformly from the super-topic vocabulary,
+    10 % from a global Zipf background (measured at 1 M passages through the 6-layer encoder: 90 % of a
+    query's exact top-10 lie in its own topic and HNSW M=32 reaches recall@10 0.94 at efSearch 64;
+    with a 70/15/15 mix the figures are 71 % and 0.85 — gpurun_out/graph_recall2.log).  With ~32 passages per topic the exact top-10 of a query are
     concentrated in its topic while neighbouring topics stay closer than unrelated ones — the local
     structure real text embeddings have and i.i.d. bags of words lack."""
 
@@ -165,7 +167,7 @@ class TopicModel:
         self.zipf_perm = rng.permutation(nwords).astype(np.int32) + FIRST_WORD_ID
 
     def sample(self, n: int, seed: int, len_mean: float, len_std: float, len_min: int, len_max: int,
-               p_topic: float = 0.70, p_super: float = 0.15) -> Corpus:
+               p_topic: float = 0.80, p_super: float = 0.10) -> Corpus:
         rng = np.random.default_rng(seed)
         topics = rng.integers(0, self.n_topics, n).astype(np.int32)
         lens = np.clip(np.rint(rng.normal(len_mean, len_std, n)), len_min, len_max).astype(np.int64)
@@ -193,12 +195,12 @@ class TopicModel:
 
 
 def make_corpus(n: int, vocab_size: int = 30522, seed: int = 1234, max_len: int = 256, n_topics: int | None = None,
-                p_topic: float = 0.70, p_super: float = 0.15):
+                p_topic: float = 0.80, p_super: float = 0.10):
     tm = TopicModel(vocab_size, n_topics or max(4, n // 32), seed)
     corpus = tm.sample(n, seed + 1, 128, 48, 16, max_len, p_topic, p_super)
     return tm, corpus
 
 
-def make_queries(tm: TopicModel, nq: int, seed: int = 4321, len_mean: float = 24, p_topic: float = 0.70,
-                 p_super: float = 0.15) -> Corpus:
+def make_queries(tm: TopicModel, nq: int, seed: int = 4321, len_mean: float = 32, p_topic: float = 0.80,
+                 p_super: float = 0.10) -> Corpus:
     return tm.sample(nq, seed, len_mean, len_mean / 3, 4, 64, p_topic, p_super)
