@@ -147,9 +147,13 @@ int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const 
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);
 int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden,
                            float eps);
-/* qkv: packed [sum(len), 3*hidden] fp16; d_seq_start / d_seq_len: device int32[n_seq] (first row, length) */
+/* qkv: HEAD-MAJOR packed [heads][n_tokens][3*head_dim] fp16 (q|k|v per token), n_tokens = sum(len);
+ * d_seq_start / d_seq_len: device int32[n_seq] (first row, length); ctx: [n_tokens, hidden] */
 int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq,
-                           int hidden, int heads, int max_len, void* dctx);
+                           int n_tokens, int hidden, int heads, int max_len, void* dctx);
+/* grouped-output GEMM (the QKV projection): C is [N / c_group][M][c_group] */
+int lb2_test_gemm_grouped_f16(const void* dA, const void* dW, const float* dbias, void* dC, int M, int N, int K,
+                              int c_group);
 
 #ifdef __cplusplus
 }

@@ -658,6 +658,17 @@ int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const 
     return LB2_OK;
 }
 
+int lb2_test_gemm_grouped_f16(const void* dA, const void* dW, const float* dbias, void* dC, int M, int N, int K, int c_group) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!gemm_f16(0, (const __half*)dA, nullptr, (const __half*)dW, dbias, nullptr, (__half*)dC, M, N, K, EPI_BIAS, sms, c_group))
+        return LB2_ERR_CUDA;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
+    return LB2_OK;
+}
+
 int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden, float eps) {
     if (!launch_layernorm(0, (const __half*)din, dg, db, (__half*)dout, rows, hidden, eps)) return LB2_ERR_CUDA;
     cudaError_t e = cudaDeviceSynchronize();
@@ -665,9 +676,9 @@ int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, vo
     return LB2_OK;
 }
 
-int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq, int hidden,
-                           int heads, int max_len, void* dctx) {
-    const bool ok = launch_attention(0, (const __half*)dqkv, d_seq_start, d_seq_len, 0, max_len, n_seq, hidden, heads, (__half*)dctx);
+int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq, int n_tokens,
+                           int hidden, int heads, int max_len, void* dctx) {
+    const bool ok = launch_attention(0, (const __half*)dqkv, d_seq_start, d_seq_len, 0, max_len, n_seq, n_tokens, hidden, heads, (__half*)dctx);
     cudaError_t e = cudaDeviceSynchronize();
     if (!ok) return LB2_ERR_CUDA;
     if (e != cudaSuccess) { set_error("attention: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }

@@ -25,7 +25,7 @@ enum Epilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2 };
 bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols = 64);
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
-              const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms);
+              const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms, int c_group = 0);
 int gemm_block_n();
 // optional per-kernel-class timing with CUDA events (api.cu owns the pools; no-ops unless
 // LB2_PROFILE_GEMM=1): category 0 = tcgen05 GEMMs, 1 = attention, 2 = LayerNorm / embed / pool
@@ -83,7 +83,8 @@ bool encoder_forward(Encoder* enc, cudaStream_t stream, const uint16_t* tok_stor
 // kernels exposed for the unit-test hooks in api.cu
 bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const float* b, __half* out, int rows,
                       int hidden, float eps);
+// qkv is head-major: [heads][n_tokens][3 * head_dim] (q | k | v per token)
 bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
-                      int max_pos, int n_seq, int hidden, int heads, __half* ctx);
+                      int max_pos, int n_seq, int n_tokens, int hidden, int heads, __half* ctx);
 
 }  // namespace lb2

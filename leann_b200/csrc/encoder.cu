@@ -176,22 +176,26 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // One CTA = (sequence, head, block of 64 query rows); 4 warps x 16 rows.  Keys/values stream through a
 // double-buffered 64-key smem ring filled with cp.async (zero-fill past L), so the CTA's footprint is
 // 20 KB whatever the sequence length and several CTAs per SM overlap each other's load latency.
+// Input is HEAD-MAJOR: qkv[head][token][q(hd) | k(hd) | v(hd)], written that way by the QKV GEMM's
+// grouped TMA store, so one (sequence, head) is a single contiguous run of L * 3hd halves: every DRAM
+// line fetched is fully used (the token-major layout cost 2.7x the algorithmic DRAM reads, ncu).
+// blockIdx.x = query block, so the CTAs sharing a (sequence, head)'s keys are launched back to back.
 template <int HD>
 __global__ void __launch_bounds__(128, 6)
 attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq_start,
-                 const int32_t* __restrict__ seq_len, int row_base, int hidden, __half* __restrict__ ctx) {
+                 const int32_t* __restrict__ seq_len, int row_base, int n_tokens, int hidden, __half* __restrict__ ctx) {
     constexpr int P = HD + 8;  // row pitch in halves: 16-byte aligned rows, conflict-free ldmatrix
     __shared__ __align__(16) __half Ks[2][64 * P];
     __shared__ __align__(16) __half Vs[2][64 * P];
-    const int s = blockIdx.x, h = blockIdx.y;
+    const int s = blockIdx.z, h = blockIdx.y;
     const int L = seq_len[s];
-    const int qblk0 = blockIdx.z * 64;
+    const int qblk0 = blockIdx.x * 64;
     if (qblk0 >= L) return;
     const int row0 = seq_start[s] - row_base;
-    const int ld = 3 * hidden;
-    const __half* qbase = qkv + static_cast<size_t>(row0) * ld + h * HD;
-    const __half* kbase = qbase + hidden;
-    const __half* vbase = qbase + 2 * hidden;
+    constexpr int ld = 3 * HD;
+    const __half* qbase = qkv + (static_cast<size_t>(h) * n_tokens + row0) * ld;
+    const __half* kbase = qbase + HD;
+    const __half* vbase = qbase + 2 * HD;
     const int nkb = (L + 63) >> 6;
 
     auto prefetch = [&](int kb, int buf) {
@@ -388,14 +392,15 @@ bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const fl
 }
 
 bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
-                      int max_pos, int n_seq, int hidden, int heads, __half* ctx) {
+                      int max_pos, int n_seq, int n_tokens, int hidden, int heads, __half* ctx) {
     if (n_seq <= 0) return true;
     const int hd = hidden / heads;
-    dim3 grid(n_seq, heads, (max_pos + 63) / 64);
+    if (n_seq > 65535) { set_error("attention: more than 65535 passages in one pass"); return false; }
+    dim3 grid((max_pos + 63) / 64, heads, n_seq);
     if (hd == 32)
-        attention_kernel<32><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, hidden, ctx);
+        attention_kernel<32><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, n_tokens, hidden, ctx);
     else if (hd == 64)
-        attention_kernel<64><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, hidden, ctx);
+        attention_kernel<64><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, n_tokens, hidden, ctx);
     else {
         set_error("attention: unsupported head_dim %d", hd);
         return false;
@@ -478,8 +483,24 @@ bool encoder_load(Encoder* enc, const EncoderConfig& cfg, const float* w, size_t
     enc->layers = new LayerWeights[Lr];
     for (size_t l = 0; l < Lr && ok; l++) {
         LayerWeights& lw = enc->layers[l];
-        ok &= (lw.w_qkv = put16(3 * H * H)) != nullptr;
-        ok &= (lw.b_qkv = put32(3 * H)) != nullptr;
+        {   // rows of [Wq; Wk; Wv] regrouped per head (q_h | k_h | v_h) so that the GEMM output is head-major
+            const size_t hd = H / cfg.heads;
+            std::vector<float> wp(3 * H * H), bp(3 * H);
+            const float* bsrc = src + 3 * H * H;
+            for (size_t h = 0; h < (size_t)cfg.heads; h++)
+                for (size_t part = 0; part < 3; part++)
+                    for (size_t j = 0; j < hd; j++) {
+                        const size_t dst_row = h * 3 * hd + part * hd + j, src_row = part * H + h * hd + j;
+                        memcpy(&wp[dst_row * H], src + src_row * H, H * sizeof(float));
+                        bp[dst_row] = bsrc[src_row];
+                    }
+            const float* keep = src;
+            src = wp.data();
+            ok &= (lw.w_qkv = put16(3 * H * H)) != nullptr;
+            src = bp.data();
+            ok &= (lw.b_qkv = put32(3 * H)) != nullptr;
+            src = keep + 3 * H * H + 3 * H;
+        }
         ok &= (lw.w_o = put16(H * H)) != nullptr;
         ok &= (lw.b_o = put32(H)) != nullptr;
         ok &= (lw.ln1_g = put32(H)) != nullptr;
@@ -567,17 +588,17 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
     const int H = c.hidden, F = c.ffn, T = n_tokens, sms = enc->num_sms;
     if (!launch_embed_ln(st, enc, tok_store, tok_off, seq_node, seq_start, row_base, n_seq, enc->x, enc->seq_len)) return false;
     auto gemm = [&](const __half* A, const CUtensorMap* tm, const __half* W, const float* bias, const __half* res,
-                    __half* C, int N, int K, int epi) {
+                    __half* C, int N, int K, int epi, int c_group = 0) {
         prof_begin(st, PROF_GEMM);
-        const bool ok = gemm_f16(st, A, tm, W, bias, res, C, T, N, K, epi, sms);
+        const bool ok = gemm_f16(st, A, tm, W, bias, res, C, T, N, K, epi, sms, c_group);
         prof_end(st, PROF_GEMM, 2.0 * T * (double)N * K);
         return ok;
     };
     for (int l = 0; l < c.layers; l++) {
         const LayerWeights& w = enc->layers[l];
-        if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS)) return false;
+        if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS, 3 * (H / c.heads))) return false;
         prof_begin(st, PROF_ATTN);
-        if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, row_base, c.max_pos, n_seq, H, c.heads, enc->ctx)) return false;
+        if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, row_base, c.max_pos, n_seq, T, H, c.heads, enc->ctx)) return false;
         prof_end(st, PROF_ATTN, 0);
         if (!gemm(enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, enc->y, H, H, EPI_BIAS_RES)) return false;
         prof_begin(st, PROF_NORM);

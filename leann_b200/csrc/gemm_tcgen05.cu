@@ -63,7 +63,7 @@ template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                   const float* __restrict__ bias, int M, int N, int K) {
+                   const float* __restrict__ bias, int M, int N, int K, int c_group) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                             : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -248,7 +248,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 ptx::fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::tma_store_2d(&tmap_c, stage_buf + c * 2048, col0, row0);
+                    if (c_group > 0)  // grouped (head-major) output [N / c_group][M][c_group]
+                        ptx::tma_store_3d(&tmap_c, stage_buf + c * 2048, col0 % c_group, row0, col0 / c_group);
+                    else
+                        ptx::tma_store_2d(&tmap_c, stage_buf + c * 2048, col0, row0);
                     ptx::bulk_commit();
                 }
             }
@@ -310,12 +313,33 @@ bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
     return true;
 }
 
+// Output viewed as [groups][rows][group_cols] fp16 (group-major), box = [1][32 rows][32 cols], SWIZZLE_64B.
+static bool make_tmap_f16_grouped(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t group_cols, uint64_t groups) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return false;
+    }
+    cuuint64_t dims[3] = {group_cols, rows, groups};
+    cuuint64_t strides[2] = {group_cols * 2, rows * group_cols * 2};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (grouped) failed (%d) rows=%llu", (int)r, (unsigned long long)rows);
+        return false;
+    }
+    return true;
+}
+
 constexpr int GEMM_BLOCK_N = 192;
 constexpr int GEMM_STAGES = 4;
 
 template <int EPI>
 static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                               const CUtensorMap& tr, const float* bias, int M, int N, int K, int num_sms) {
+                               const CUtensorMap& tr, const float* bias, int M, int N, int K, int c_group, int num_sms) {
     using L = GemmSmem<GEMM_BLOCK_N, GEMM_STAGES>;
     auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI>;
     static bool attr_set = false;
@@ -326,13 +350,14 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group);
     return cudaGetLastError();
 }
 
 // A [M,K] fp16 row-major, W [N,K] fp16 row-major (nn.Linear layout), C [M,N] fp16.
+// c_group > 0: C is written group-major, [N / c_group][M][c_group] (the per-head q|k|v layout attention reads).
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
-              const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms) {
+              const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms, int c_group) {
     if (M <= 0) return true;
     if (N % GEMM_BLOCK_N != 0 || K % BLOCK_K != 0) {
         set_error("gemm_f16: unsupported shape N=%d K=%d (need N%%192==0, K%%64==0)", N, K);
@@ -344,7 +369,15 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
     }
     CUtensorMap ta, tb_local, tc, tr;
     if (!make_tmap_f16_2d(&ta, A, (uint64_t)M, (uint64_t)K, BLOCK_M, BLOCK_K)) return false;
-    if (!make_tmap_f16_2d(&tc, C, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
+    if (c_group > 0) {
+        if (c_group % 32 != 0 || N % c_group != 0 || epi == EPI_BIAS_RES) {
+            set_error("gemm_f16: bad grouped output (c_group=%d N=%d)", c_group, N);
+            return false;
+        }
+        if (!make_tmap_f16_grouped(&tc, C, (uint64_t)M, (uint64_t)c_group, (uint64_t)(N / c_group))) return false;
+    } else if (!make_tmap_f16_2d(&tc, C, (uint64_t)M, (uint64_t)N, 32, 32)) {
+        return false;
+    }
     if (!make_tmap_f16_2d(&tr, epi == EPI_BIAS_RES ? residual : C, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
     if (!tmap_w) {
         if (!make_tmap_f16_2d(&tb_local, W, (uint64_t)N, (uint64_t)K, GEMM_BLOCK_N, BLOCK_K)) return false;
@@ -352,9 +385,9 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
     }
     cudaError_t e;
     switch (epi) {
-        case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
-        case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
-        case EPI_BIAS_RES: e = launch_gemm<EPI_BIAS_RES>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, num_sms); break;
+        case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
+        case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
+        case EPI_BIAS_RES: e = launch_gemm<EPI_BIAS_RES>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
         default: set_error("gemm_f16: bad epilogue %d", epi); return false;
     }
     if (e != cudaSuccess) {

@@ -43,7 +43,7 @@ for L in (64, 128, 256):
     ctx = torch.empty(n_seq * L, H, device=dev, dtype=torch.float16)
     dl = torch.full((n_seq,), L, dtype=torch.int32, device=dev)
     ds = (torch.cumsum(dl, 0) - dl).to(torch.int32)
-    dt = timeit(lambda: lib.lb2_test_attention_f16(qkv.data_ptr(), ds.data_ptr(), dl.data_ptr(), n_seq, H, heads, 256, ctx.data_ptr()), 5)
+    dt = timeit(lambda: lib.lb2_test_attention_f16(qkv.data_ptr(), ds.data_ptr(), dl.data_ptr(), n_seq, n_seq * L, H, heads, 256, ctx.data_ptr()), 5)
     fl = 4.0 * L * H * n_seq * L
     print(f"attention L={L:3d} n_seq={n_seq}: {dt*1e3:8.3f} ms  {fl/dt/1e12:7.1f} TFLOP/s  ({n_seq*L/dt/1e6:7.1f} Mtok/s)")
     del qkv, ctx

@@ -38,6 +38,20 @@ def test_gemm_tcgen05_vs_torch(lib, cuda_ok, M, N, K, epi):
     assert (err <= tol).all(), f"max err {err.max().item()} at {torch.nonzero(err > tol)[:3].tolist()}"
 
 
+@pytest.mark.parametrize("M", [5, 300, 20000])
+def test_gemm_grouped_head_major_output(lib, cuda_ok, M):
+    N, K, G = 1152, 384, 96
+    g = torch.Generator(device="cuda").manual_seed(M)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    C = torch.full((N // G, M, G), float("nan"), device="cuda", dtype=torch.float16)
+    assert lib.lb2_test_gemm_grouped_f16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), C.data_ptr(), M, N, K, G) == 0, lib.lb2_last_error()
+    ref = (A.float() @ W.float().T + bias).view(M, N // G, G).permute(1, 0, 2)
+    assert torch.isfinite(C).all()
+    assert ((C.float() - ref).abs() <= 2e-3 + 1.5e-3 * ref.abs()).all()
+
+
 def test_gemm_rejects_unsupported_shapes(lib, cuda_ok):
     A = torch.zeros(8, 100, device="cuda", dtype=torch.float16)
     rc = lib.lb2_test_gemm_f16(A.data_ptr(), A.data_ptr(), A.data_ptr(), A.data_ptr(), A.data_ptr(), 8, 100, 100, 0)
@@ -67,7 +81,9 @@ def test_attention_vs_torch(lib, cuda_ok, H, heads):
     ctx = torch.full((T, H), float("nan"), device="cuda", dtype=torch.float16)
     dl = torch.tensor(lens, dtype=torch.int32, device="cuda")
     ds = (torch.cumsum(dl, 0) - dl).to(torch.int32)
-    rc = lib.lb2_test_attention_f16(qkv.data_ptr(), ds.data_ptr(), dl.data_ptr(), len(lens), H, heads, 256, ctx.data_ptr())
+    # the kernel reads the head-major layout the QKV GEMM writes: [heads][T][q|k|v]
+    qkvh = qkv.view(T, 3, heads, hd).permute(2, 0, 1, 3).contiguous()
+    rc = lib.lb2_test_attention_f16(qkvh.data_ptr(), ds.data_ptr(), dl.data_ptr(), len(lens), T, H, heads, 256, ctx.data_ptr())
     assert rc == 0, lib.lb2_last_error()
     assert torch.isfinite(ctx).all()
     off = 0
