@@ -48,6 +48,3 @@ for L in (64, 128, 256):
     print(f"attention L={L:3d} n_seq={n_seq}: {dt*1e3:8.3f} ms  {fl/dt/1e12:7.1f} TFLOP/s  ({n_seq*L/dt/1e6:7.1f} Mtok/s)")
     del qkv, ctx
 
-x = torch.randn(T, H, device=dev).half(); g = torch.randn(H, device=dev); bb = torch.randn(H, device=dev); o = torch.empty_like(x)
-dt = timeit(lambda: lib.lb2_test_layernorm_f16(x.data_ptr(), g.data_ptr(), bb.data_ptr(), o.data_ptr(), T, H, 1e-12))
-print(f"layernorm rows={T}: {dt*1e3:8.3f} ms  {2*T*H*2/dt/1e9:7.0f} GB/s")
