@@ -59,7 +59,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI, bool LN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
@@ -184,7 +184,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int colbase = n_blk * BLOCK_N + half * NCH * 32;
             // deferred LayerNorm: this thread's row statistics (fixed-order sum of the producer's partials)
             float ln_r = 1.f, ln_nmr = 0.f;  // r and -mu * r
-            if (ea.stats_in != nullptr) {
+            if (LN) {
                 const int grow = row0 + lane;
                 if (grow < M) {
                     const float2* sp = reinterpret_cast<const float2*>(ea.stats_in) + static_cast<size_t>(grow) * ea.parts_in;
@@ -231,8 +231,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     __syncwarp();
                 }
                 const float4* bp = reinterpret_cast<const float4*>(ea.bias + col0);
-                const bool ln_in = (EPI != EPI_BIAS_RES) && ea.stats_in != nullptr;
-                const bool ln_res = (EPI == EPI_BIAS_RES) && ea.ln_g != nullptr;
+                constexpr bool ln_in = LN && (EPI != EPI_BIAS_RES);
+                constexpr bool ln_res = LN && (EPI == EPI_BIAS_RES);
                 const float4* sp4 = reinterpret_cast<const float4*>((ln_in ? ea.svec : ea.bias) + col0);
                 const float4* gp4 = reinterpret_cast<const float4*>((ln_res ? ea.ln_g : ea.bias) + col0);
                 const float4* lb4 = reinterpret_cast<const float4*>((ln_res ? ea.ln_b : ea.bias) + col0);
@@ -245,12 +245,15 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const float4 b4 = __ldg(bp + 2 * j4 + u);  // warp-uniform address: one broadcast transaction
                         float a0 = __uint_as_float(acc[8 * j4 + 4 * u + 0]), a1 = __uint_as_float(acc[8 * j4 + 4 * u + 1]);
                         float a2 = __uint_as_float(acc[8 * j4 + 4 * u + 2]), a3 = __uint_as_float(acc[8 * j4 + 4 * u + 3]);
-                        if (ln_in) {  // r * (acc - mu * s) = r * acc + (-mu r) * s
+                        if (ln_in) {  // r * (acc - mu * s) + t = r * acc + ((-mu r) * s + t): two FMAs per element
                             const float4 s4 = __ldg(sp4 + 2 * j4 + u);
-                            a0 = fmaf(ln_r, a0, ln_nmr * s4.x); a1 = fmaf(ln_r, a1, ln_nmr * s4.y);
-                            a2 = fmaf(ln_r, a2, ln_nmr * s4.z); a3 = fmaf(ln_r, a3, ln_nmr * s4.w);
+                            v[4 * u + 0] = fmaf(ln_r, a0, fmaf(ln_nmr, s4.x, b4.x));
+                            v[4 * u + 1] = fmaf(ln_r, a1, fmaf(ln_nmr, s4.y, b4.y));
+                            v[4 * u + 2] = fmaf(ln_r, a2, fmaf(ln_nmr, s4.z, b4.z));
+                            v[4 * u + 3] = fmaf(ln_r, a3, fmaf(ln_nmr, s4.w, b4.w));
+                        } else {
+                            v[4 * u + 0] = a0 + b4.x; v[4 * u + 1] = a1 + b4.y; v[4 * u + 2] = a2 + b4.z; v[4 * u + 3] = a3 + b4.w;
                         }
-                        v[4 * u + 0] = a0 + b4.x; v[4 * u + 1] = a1 + b4.y; v[4 * u + 2] = a2 + b4.z; v[4 * u + 3] = a3 + b4.w;
                     }
                     if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
@@ -284,7 +287,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
                     for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
                     if (EPI == EPI_BIAS_RES) {
-                        if (ea.stats_out != nullptr) {  // statistics of the values actually stored (fp16-rounded)
+                        if (LN) {  // statistics of the values actually stored (fp16-rounded)
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
                                 const float2 t2 = __half22float2(oh[u]);
@@ -306,7 +309,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 }
             }
             if (EPI == EPI_BIAS_RES) {
-                if (ea.stats_out != nullptr && row0 + lane < M) {
+                if (LN && ea.stats_out != nullptr && row0 + lane < M) {
                     // slot = which 96-column slice of the row this warp covered
                     const int parts_out = N / (NCH * 32);
                     float2* so = reinterpret_cast<float2*>(ea.stats_out) + static_cast<size_t>(row0 + lane) * parts_out;
@@ -395,11 +398,11 @@ static bool make_tmap_f16_grouped(CUtensorMap* map, const void* ptr, uint64_t ro
 constexpr int GEMM_BLOCK_N = 192;
 constexpr int GEMM_STAGES = 4;
 
-template <int EPI>
+template <int EPI, bool LN>
 static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                                const CUtensorMap& tr, const EpiArgs& ea, int M, int N, int K, int c_group, int num_sms) {
     using L = GemmSmem<GEMM_BLOCK_N, GEMM_STAGES>;
-    auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI>;
+    auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI, LN>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -447,12 +450,20 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
         tmap_w = &tb_local;
     }
     cudaError_t e;
+    const bool ln = ea.stats_in != nullptr;  // deferred-LayerNorm epilogue (LN-in for epilogues 0/1, LN-res for 2)
+    if (ln && epi == EPI_BIAS_RES && (!ea.ln_g || !ea.stats_out)) {
+        set_error("gemm_f16: LN-res epilogue needs ln_g / ln_b / stats_out");
+        return false;
+    }
+#define LB2_LAUNCH(E) (ln ? launch_gemm<E, true>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms) \
+                          : launch_gemm<E, false>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms))
     switch (epi) {
-        case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms); break;
-        case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms); break;
-        case EPI_BIAS_RES: e = launch_gemm<EPI_BIAS_RES>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms); break;
+        case EPI_BIAS: e = LB2_LAUNCH(EPI_BIAS); break;
+        case EPI_BIAS_GELU: e = LB2_LAUNCH(EPI_BIAS_GELU); break;
+        case EPI_BIAS_RES: e = LB2_LAUNCH(EPI_BIAS_RES); break;
         default: set_error("gemm_f16: bad epilogue %d", epi); return false;
     }
+#undef LB2_LAUNCH
     if (e != cudaSuccess) {
         set_error("gemm_f16 launch: %s", cudaGetErrorString(e));
         return false;
