@@ -56,6 +56,63 @@ def _knn(xq: torch.Tensor, xb: torch.Tensor, k: int, metric_ip: bool, self_pos: 
 
 
 @torch.no_grad()
+def _knn_ivf(x: torch.Tensor, k: int, metric_ip: bool, n_clusters: int | None = None, n_probe: int = 12,
+             seed: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+    """Approximate kNN of every row among all rows for large n: k-means partition, then exact search of each
+    cluster's members inside the `n_probe` clusters nearest to its centroid (~n_probe / n_clusters of the
+    data).  Same return convention as _knn (self excluded)."""
+    n, d = x.shape
+    dev = x.device
+    C = n_clusters or int(round((n / 10000) ** 0.5 * 32))  # ~1000 clusters at 10 M
+    C = max(8, min(C, n // 64))
+    g = torch.Generator(device=dev).manual_seed(seed)
+    samp = x[torch.randint(0, n, (min(n, 256 * C),), device=dev, generator=g)]
+    cent = samp[torch.randperm(samp.shape[0], device=dev, generator=g)[:C]].clone()
+    for _ in range(8):  # Lloyd iterations on the sample
+        sc = samp @ cent.T if metric_ip else -(torch.cdist(samp, cent) ** 2)
+        a = sc.argmax(1)
+        cent.zero_().index_add_(0, a, samp)
+        cnt = torch.bincount(a, minlength=C).clamp(min=1).unsqueeze(1)
+        cent = cent / cnt
+        if metric_ip:
+            cent = torch.nn.functional.normalize(cent, dim=1)
+    assign = torch.empty(n, dtype=torch.int64, device=dev)
+    for b0 in range(0, n, 1 << 18):
+        xb = x[b0:b0 + (1 << 18)]
+        sc = xb @ cent.T if metric_ip else -(torch.cdist(xb, cent) ** 2)
+        assign[b0:b0 + (1 << 18)] = sc.argmax(1)
+    order = torch.argsort(assign, stable=True)
+    counts = torch.bincount(assign, minlength=C)
+    starts = torch.cumsum(counts, 0) - counts
+    csc = cent @ cent.T if metric_ip else -(torch.cdist(cent, cent) ** 2)
+    probes = torch.topk(csc, min(n_probe, C), dim=1).indices  # includes the cluster itself
+    xs = x.half()
+    sq = (x * x).sum(1)
+    k = min(k, n - 1)
+    idx = torch.empty((n, k), dtype=torch.int64, device=dev)
+    dist = torch.full((n, k), float("inf"), dtype=torch.float32, device=dev)
+    counts_h, starts_h = counts.tolist(), starts.tolist()
+    for c in range(C):
+        if counts_h[c] == 0:
+            continue
+        qi = order[starts_h[c]: starts_h[c] + counts_h[c]]
+        bi = torch.cat([order[starts_h[p]: starts_h[p] + counts_h[p]] for p in probes[c].tolist()])
+        xb = xs[bi]
+        kk = min(k, bi.numel() - 1)
+        for q0 in range(0, qi.numel(), 8192):
+            qq = qi[q0:q0 + 8192]
+            ip = (xs[qq] @ xb.T).float()
+            dm = -ip if metric_ip else (sq[qq][:, None] + sq[bi][None, :] - 2 * ip)
+            dm[qq[:, None] == bi[None, :]] = float("inf")  # exclude self
+            dv, di = torch.topk(dm, kk, dim=1, largest=False)
+            idx[qq, :kk] = bi[di]
+            dist[qq, :kk] = dv
+            if kk < k:
+                idx[qq, kk:] = -1
+    return idx, dist
+
+
+@torch.no_grad()
 def _heuristic_prune(x: torch.Tensor, cand: torch.Tensor, cdist: torch.Tensor, keep: int, metric_ip: bool,
                      fill: bool, alpha: float = 1.0, block: int = 8192) -> torch.Tensor:
     """HNSW neighbour selection over candidates sorted by distance (padding = -1 / +inf at the end);
@@ -138,7 +195,7 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
 @torch.no_grad()
 def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
                      knn_factor: float = 1.5, n_scales: int = 2, alpha: float = 1.0, union_factor: int = 2,
-                     verbose: bool = False) -> CSRGraph:
+                     ivf_threshold: int = 2_500_000, verbose: bool = False) -> CSRGraph:
     metric_ip = metric.lower() in ("mips", "cosine", "ip")
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
     x = emb if isinstance(emb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(emb, np.float32))
@@ -160,7 +217,10 @@ def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, 
             # multi-scale candidates: nearest members, plus nearest among the (sparser) members of
             # the next levels up.  The sparse samples play the role of HNSW's early insertions and
             # supply the long links a pure kNN graph lacks.
-            ci, cd = _knn(xm, xm, int(cap * knn_factor), metric_ip, torch.arange(nm, device=dev))
+            if nm > ivf_threshold:  # brute force is O(n^2): partition-restricted search beyond a few million points
+                ci, cd = _knn_ivf(xm, int(cap * knn_factor), metric_ip)
+            else:
+                ci, cd = _knn(xm, xm, int(cap * knn_factor), metric_ip, torch.arange(nm, device=dev))
             cis, cds = [ci], [cd]
             for s_up in range(1, n_scales + 1):
                 sub = np.nonzero(levels[members] > l + s_up)[0]
