@@ -145,13 +145,8 @@ int lb2_configure(lb2_index* idx, int32_t slots, int32_t passages_per_pass);
 /* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
 int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);
-/* deferred-LayerNorm epilogues (see EpiArgs in csrc/common.cuh): LN-in (epilogue 0/1: the GEMM ran on pre-LN
- * rows with gamma-folded weights; stats_in = [M][2*parts_in] partial (sum, sumsq) of the A rows, svec = row sums
- * of the folded weights, bias = folded bias) and LN-res (epilogue 2: the residual rows are pre-LN, normalised
- * with stats_in / ln_g / ln_b on the fly; stats_out = [M][2*N/96] partial statistics of the rows written). */
-int lb2_test_gemm_ln_f16(const void* dA, const void* dW, const float* dbias, const float* dsvec, const float* dstats_in,
-                         int parts_in, int ln_width, const void* dres, const float* dln_g, const float* dln_b,
-                         float* dstats_out, void* dC, int M, int N, int K, int epilogue);
+int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden,
+                           float eps);
 /* qkv: HEAD-MAJOR packed [heads][n_tokens][3*head_dim] fp16 (q|k|v per token), n_tokens = sum(len);
  * d_seq_start / d_seq_len: device int32[n_seq] (first row, length); ctx: [n_tokens, hidden] */
 int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq,

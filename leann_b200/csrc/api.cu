@@ -247,7 +247,7 @@ int next_pow2(int v) {
     return p;
 }
 
-int encoder_kernels_per_pass(const Encoder& e) { return 2 + e.cfg.layers * 5; }  // embed, pool, 4 GEMMs + attention per layer
+int encoder_kernels_per_pass(const Encoder& e) { return 2 + e.cfg.layers * 7; }
 
 int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
                 const lb2_search_params* prm, lb2_search_stats* stats) {
@@ -646,38 +646,34 @@ int lb2_encode_tokens(lb2_index* x, int64_t n, const uint16_t* tokens, const uin
 }
 
 // ---------------------------------------------------------------- unit-test hooks
-static int run_test_gemm(const void* dA, const void* dW, const EpiArgs& ea, const void* dres, void* dC, int M, int N, int K,
-                         int epi, int c_group) {
+int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
+                      int K, int epi) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!gemm_f16(0, (const __half*)dA, nullptr, (const __half*)dW, ea, (const __half*)dres, (__half*)dC, M, N, K, epi, sms, c_group))
+    if (!gemm_f16(0, (const __half*)dA, nullptr, (const __half*)dW, dbias, (const __half*)dres, (__half*)dC, M, N, K, epi, sms))
         return LB2_ERR_CUDA;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     return LB2_OK;
 }
 
-int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
-                      int K, int epi) {
-    EpiArgs ea;
-    ea.bias = dbias;
-    return run_test_gemm(dA, dW, ea, dres, dC, M, N, K, epi, 0);
-}
-
 int lb2_test_gemm_grouped_f16(const void* dA, const void* dW, const float* dbias, void* dC, int M, int N, int K, int c_group) {
-    EpiArgs ea;
-    ea.bias = dbias;
-    return run_test_gemm(dA, dW, ea, nullptr, dC, M, N, K, EPI_BIAS, c_group);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!gemm_f16(0, (const __half*)dA, nullptr, (const __half*)dW, dbias, nullptr, (__half*)dC, M, N, K, EPI_BIAS, sms, c_group))
+        return LB2_ERR_CUDA;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
+    return LB2_OK;
 }
 
-int lb2_test_gemm_ln_f16(const void* dA, const void* dW, const float* dbias, const float* dsvec, const float* dstats_in,
-                         int parts_in, int ln_width, const void* dres, const float* dln_g, const float* dln_b,
-                         float* dstats_out, void* dC, int M, int N, int K, int epi) {
-    EpiArgs ea;
-    ea.bias = dbias; ea.svec = dsvec; ea.stats_in = dstats_in; ea.parts_in = parts_in; ea.ln_g = dln_g; ea.ln_b = dln_b;
-    ea.stats_out = dstats_out; ea.inv_width = 1.0f / (float)ln_width; ea.eps = 1e-12f;
-    return run_test_gemm(dA, dW, ea, dres, dC, M, N, K, epi, 0);
+int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden, float eps) {
+    if (!launch_layernorm(0, (const __half*)din, dg, db, (__half*)dout, rows, hidden, eps)) return LB2_ERR_CUDA;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("layernorm: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
+    return LB2_OK;
 }
 
 int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq, int n_tokens,

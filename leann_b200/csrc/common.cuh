@@ -21,32 +21,10 @@ void set_error(const char* fmt, ...);
 
 enum Epilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2 };
 
-// Epilogue operands of the tcgen05 GEMM.  With the "deferred LayerNorm" fields set, the LayerNorms of
-// the BERT block never run as kernels: a producer GEMM (EPI_BIAS_RES) emits per-row partial
-// (sum, sum of squares) of the pre-LN tensor it writes, and the consumers apply the normalisation
-// algebraically —
-//   LN-in  (EPI_BIAS / EPI_BIAS_GELU, stats_in != null):  the GEMM ran on the PRE-LN rows y with weights
-//           W' = W * gamma folded in, so   out = r * (acc - mu * svec[n]) + bias[n],
-//           svec[n] = sum_k W'[n,k],  bias[n] = sum_k beta[k] W[n,k] + b[n]   (precomputed at load time);
-//   LN-res (EPI_BIAS_RES, ln_g != null):  the residual tile holds pre-LN rows p, used as
-//           (p - mu) * r * gamma[n] + beta[n].
-// Partials are kept in fixed slots and summed in a fixed order (no atomics): results stay bit-reproducible.
-struct EpiArgs {
-    const float* bias = nullptr;      // [N]
-    const float* svec = nullptr;      // [N]   LN-in only
-    const float* stats_in = nullptr;  // [M][2 * parts_in]  stats of the A rows (LN-in) or of the residual rows (LN-res)
-    int parts_in = 0;
-    const float* ln_g = nullptr;      // [N]   LN-res only
-    const float* ln_b = nullptr;      // [N]
-    float* stats_out = nullptr;       // [M][2 * (N / 96)]  EPI_BIAS_RES only: partial stats of the rows written
-    float inv_width = 0.f;            // 1 / (normalised width of the incoming LN)
-    float eps = 1e-12f;
-};
-
 // ---- gemm_tcgen05.cu
 bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols = 64);
-bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const EpiArgs& ea,
+bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms, int c_group = 0);
 int gemm_block_n();
 // optional per-kernel-class timing with CUDA events (api.cu owns the pools; no-ops unless
@@ -64,14 +42,13 @@ struct EncoderConfig {
 };
 
 struct LayerWeights {
-    __half* w_qkv;  // [3H, H]  rows regrouped per head (q_h | k_h | v_h), gamma of the incoming LN folded in
-    float* t_qkv;   // [3H]     folded bias: sum_k beta[k] W[n,k] + b[n]
-    float* s_qkv;   // [3H]     row sums of the folded (fp16) weights
+    __half* w_qkv;  // [3H, H]
+    float* b_qkv;   // [3H]
     __half* w_o;    // [H, H]
     float* b_o;
     float *ln1_g, *ln1_b;
-    __half* w_1;  // [F, H]   gamma of LN1 folded in
-    float *t_1, *s_1;
+    __half* w_1;  // [F, H]
+    float* b_1;
     __half* w_2;  // [H, F]
     float* b_2;
     float *ln2_g, *ln2_b;
@@ -85,15 +62,10 @@ struct Encoder {
     float *emb_ln_g = nullptr, *emb_ln_b = nullptr;
     LayerWeights* layers = nullptr;  // host array of device pointers
     void* arena = nullptr;           // one device allocation holding every tensor above
-    // workspaces, sized for `cap_tokens` packed tokens / `cap_seqs` passages.  p[] are the PRE-LayerNorm
-    // residual-stream tensors (the LayerNorms are applied algebraically by their consumers, see EpiArgs),
-    // st[] the per-row partial (sum, sum of squares) that go with them.
+    // workspaces, sized for `cap_tokens` packed tokens / `cap_seqs` sequences
     int64_t cap_tokens = 0, cap_seqs = 0;
-    __half* p[3] = {nullptr, nullptr, nullptr};
-    float* st[3] = {nullptr, nullptr, nullptr};
-    __half *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
+    __half *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
     int32_t* seq_len = nullptr;  // [cap_seqs] truncated passage lengths of the current pass
-    int parts = 4;               // partial-statistics slots per row = hidden / 96
     int num_sms = 148;
 };
 
@@ -109,6 +81,8 @@ bool encoder_forward(Encoder* enc, cudaStream_t stream, const uint16_t* tok_stor
                      float* out);
 
 // kernels exposed for the unit-test hooks in api.cu
+bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const float* b, __half* out, int rows,
+                      int hidden, float eps);
 // qkv is head-major: [heads][n_tokens][3 * head_dim] (q | k | v per token)
 bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
                       int max_pos, int n_seq, int n_tokens, int hidden, int heads, __half* ctx);

@@ -31,18 +31,16 @@ __device__ __forceinline__ int passage_len(const uint64_t* tok_off, int node, in
 }
 
 // ---------------------------------------------------------------------------------------
-// embeddings: word + position + token_type(0), written PRE-LayerNorm in fp16 together with the row's
-// (sum, sum of squares): the embedding LayerNorm is applied by its consumers (QKV GEMM epilogue,
-// out-proj residual), like every other LayerNorm of the stack (see EpiArgs in common.cuh).
+// embeddings: word + position + token_type(0) -> LayerNorm -> fp16   (BertEmbeddings)
 // one block per sequence, one warp per token, VPL = hidden/32 values per lane
 // ---------------------------------------------------------------------------------------
 template <int VPL>
 __global__ void __launch_bounds__(256)
-embed_kernel(const uint16_t* __restrict__ tok_store, const uint64_t* __restrict__ tok_off,
-             const int32_t* __restrict__ seq_node, const int32_t* __restrict__ seq_start, int row_base, int max_pos,
-             const __half* __restrict__ word_emb, const __half* __restrict__ pos_emb,
-             const __half* __restrict__ type_emb, __half* __restrict__ x, float* __restrict__ stats, int parts,
-             int32_t* __restrict__ seq_len_out) {
+embed_ln_kernel(const uint16_t* __restrict__ tok_store, const uint64_t* __restrict__ tok_off,
+                const int32_t* __restrict__ seq_node, const int32_t* __restrict__ seq_start, int row_base,
+                int max_pos, const __half* __restrict__ word_emb, const __half* __restrict__ pos_emb,
+                const __half* __restrict__ type_emb, const float* __restrict__ g, const float* __restrict__ b,
+                float eps, __half* __restrict__ x, int32_t* __restrict__ seq_len_out) {
     constexpr int H = VPL * 32;
     const int s = blockIdx.x;
     const int node = seq_node[s];
@@ -53,8 +51,8 @@ embed_kernel(const uint16_t* __restrict__ tok_store, const uint64_t* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     for (int p = warp; p < len; p += nwarp) {
         const int tok = toks[p];
-        float sum = 0.f, sq = 0.f;
-        __half* out = x + static_cast<size_t>(row0 + p) * H;
+        float v[VPL];
+        float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL / 4; i++) {
             const int e = (i * 32 + lane) * 4;
@@ -64,24 +62,73 @@ embed_kernel(const uint16_t* __restrict__ tok_store, const uint64_t* __restrict_
             const __half2* wh = reinterpret_cast<const __half2*>(&w);
             const __half2* ph = reinterpret_cast<const __half2*>(&pp);
             const __half2* th = reinterpret_cast<const __half2*>(&tt);
-            uint2 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const float2 a = __half22float2(wh[j]), c = __half22float2(ph[j]), d = __half22float2(th[j]);
-                oh[j] = __floats2half2_rn(a.x + c.x + d.x, a.y + c.y + d.y);
-                const float2 r = __half22float2(oh[j]);  // statistics of the stored (rounded) values
-                sum += r.x + r.y;
-                sq = fmaf(r.x, r.x, fmaf(r.y, r.y, sq));
+                v[i * 4 + 2 * j] = a.x + c.x + d.x;
+                v[i * 4 + 2 * j + 1] = a.y + c.y + d.y;
+                sum += v[i * 4 + 2 * j] + v[i * 4 + 2 * j + 1];
             }
+        }
+        const float mean = warp_sum(sum) * (1.0f / H);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; i++) { const float d = v[i] - mean; sq += d * d; }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+        __half* out = x + static_cast<size_t>(row0 + p) * H;
+#pragma unroll
+        for (int i = 0; i < VPL / 4; i++) {
+            const int e = (i * 32 + lane) * 4;
+            const float4 gg = *reinterpret_cast<const float4*>(g + e);
+            const float4 bb = *reinterpret_cast<const float4*>(b + e);
+            uint2 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+            oh[0] = __floats2half2_rn((v[i * 4] - mean) * rstd * gg.x + bb.x, (v[i * 4 + 1] - mean) * rstd * gg.y + bb.y);
+            oh[1] = __floats2half2_rn((v[i * 4 + 2] - mean) * rstd * gg.z + bb.z, (v[i * 4 + 3] - mean) * rstd * gg.w + bb.w);
             *reinterpret_cast<uint2*>(out + e) = o;
         }
-        sum = warp_sum(sum);
-        sq = warp_sum(sq);
-        if (lane < parts) {
-            float2* sp = reinterpret_cast<float2*>(stats) + static_cast<size_t>(row0 + p) * parts;
-            sp[lane] = lane == 0 ? make_float2(sum, sq) : make_float2(0.f, 0.f);
-        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over rows of a fp16 matrix (input already holds dense+bias+residual), one warp per row
+// ---------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ in, const float* __restrict__ g, const float* __restrict__ b,
+                 __half* __restrict__ out, int rows, float eps) {
+    constexpr int H = VPL * 32;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const __half* ip = in + static_cast<size_t>(row) * H;
+    float v[VPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL / 4; i++) {
+        const int e = (i * 32 + lane) * 4;
+        const uint2 w = *reinterpret_cast<const uint2*>(ip + e);
+        const __half2* wh = reinterpret_cast<const __half2*>(&w);
+        const float2 a = __half22float2(wh[0]), c = __half22float2(wh[1]);
+        v[i * 4] = a.x; v[i * 4 + 1] = a.y; v[i * 4 + 2] = c.x; v[i * 4 + 3] = c.y;
+        sum += a.x + a.y + c.x + c.y;
+    }
+    const float mean = warp_sum(sum) * (1.0f / H);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) { const float d = v[i] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+    __half* op = out + static_cast<size_t>(row) * H;
+#pragma unroll
+    for (int i = 0; i < VPL / 4; i++) {
+        const int e = (i * 32 + lane) * 4;
+        const float4 gg = *reinterpret_cast<const float4*>(g + e);
+        const float4 bb = *reinterpret_cast<const float4*>(b + e);
+        uint2 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+        oh[0] = __floats2half2_rn((v[i * 4] - mean) * rstd * gg.x + bb.x, (v[i * 4 + 1] - mean) * rstd * gg.y + bb.y);
+        oh[1] = __floats2half2_rn((v[i * 4 + 2] - mean) * rstd * gg.z + bb.z, (v[i * 4 + 3] - mean) * rstd * gg.w + bb.w);
+        *reinterpret_cast<uint2*>(op + e) = o;
     }
 }
 
@@ -269,47 +316,29 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq
 }
 
 // ---------------------------------------------------------------------------------------
-// final LayerNorm (applied on the fly from the row statistics) + pooling + L2 normalisation:
-// mean_t LN(y_t) = mean_t[(y_t - mu_t) r_t] * gamma + beta.  One CTA of 128 threads per sequence, fp32 out.
+// pooling (+ L2 normalisation): one CTA of 128 threads per sequence, fp32 output
 // ---------------------------------------------------------------------------------------
 template <int EPT>  // elements per thread = hidden / 128
 __global__ void __launch_bounds__(128)
-pool_kernel(const __half* __restrict__ y, const float* __restrict__ stats, int parts, const float* __restrict__ g,
-            const float* __restrict__ b, float eps, const int32_t* __restrict__ seq_start,
+pool_kernel(const __half* __restrict__ x, const int32_t* __restrict__ seq_start,
             const int32_t* __restrict__ seq_len, int row_base, int pooling, int normalize, float* __restrict__ out) {
     constexpr int H = EPT * 128;
     __shared__ float red[4];
     const int s = blockIdx.x;
     const int L = seq_len[s];
-    const int row0 = seq_start[s] - row_base;
-    const __half* yp = y + static_cast<size_t>(row0) * H;
-    const float2* sp = reinterpret_cast<const float2*>(stats) + static_cast<size_t>(row0) * parts;
+    const __half* xp = x + static_cast<size_t>(seq_start[s] - row_base) * H;
     float acc[EPT];
 #pragma unroll
     for (int i = 0; i < EPT; i++) acc[i] = 0.f;
     const int n = pooling == 1 ? 1 : L;
     for (int p = 0; p < n; p++) {
-        float ssum = 0.f, ssq = 0.f;
-        for (int pi = 0; pi < parts; pi++) {
-            const float2 pv = __ldg(sp + static_cast<size_t>(p) * parts + pi);
-            ssum += pv.x;
-            ssq += pv.y;
-        }
-        const float mu = ssum * (1.0f / H);
-        const float r = rsqrtf(fmaxf(ssq * (1.0f / H) - mu * mu, 0.f) + eps);
-        const float nmr = -mu * r;
 #pragma unroll
-        for (int i = 0; i < EPT; i++)
-            acc[i] += fmaf(__half2float(yp[static_cast<size_t>(p) * H + i * 128 + threadIdx.x]), r, nmr);
+        for (int i = 0; i < EPT; i++) acc[i] += __half2float(xp[static_cast<size_t>(p) * H + i * 128 + threadIdx.x]);
     }
     const float inv = 1.0f / static_cast<float>(n > 0 ? n : 1);
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < EPT; i++) {
-        const int col = i * 128 + threadIdx.x;
-        acc[i] = fmaf(acc[i] * inv, g[col], b[col]);
-        sq += acc[i] * acc[i];
-    }
+    for (int i = 0; i < EPT; i++) { acc[i] *= inv; sq += acc[i] * acc[i]; }
     float scale = 1.0f;
     if (normalize) {
         sq = warp_sum(sq);
@@ -329,17 +358,35 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ---------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------
-static bool launch_embed(cudaStream_t s, const Encoder* enc, const uint16_t* tok_store, const uint64_t* tok_off,
-                         const int32_t* seq_node, const int32_t* seq_start, int row_base, int n_seq, __half* x,
-                         float* stats) {
+bool launch_embed_ln(cudaStream_t s, const Encoder* enc, const uint16_t* tok_store, const uint64_t* tok_off,
+                     const int32_t* seq_node, const int32_t* seq_start, int row_base, int n_seq, __half* x,
+                     int32_t* seq_len_out) {
     if (n_seq <= 0) return true;
     const EncoderConfig& c = enc->cfg;
     if (c.hidden == 384)
-        embed_kernel<12><<<n_seq, 256, 0, s>>>(tok_store, tok_off, seq_node, seq_start, row_base, c.max_pos, enc->word_emb,
-                                               enc->pos_emb, enc->type_emb, x, stats, enc->parts, enc->seq_len);
+        embed_ln_kernel<12><<<n_seq, 256, 0, s>>>(tok_store, tok_off, seq_node, seq_start, row_base, c.max_pos,
+                                                   enc->word_emb, enc->pos_emb, enc->type_emb, enc->emb_ln_g,
+                                                   enc->emb_ln_b, c.ln_eps, x, seq_len_out);
     else
-        embed_kernel<24><<<n_seq, 256, 0, s>>>(tok_store, tok_off, seq_node, seq_start, row_base, c.max_pos, enc->word_emb,
-                                               enc->pos_emb, enc->type_emb, x, stats, enc->parts, enc->seq_len);
+        embed_ln_kernel<24><<<n_seq, 256, 0, s>>>(tok_store, tok_off, seq_node, seq_start, row_base, c.max_pos,
+                                                   enc->word_emb, enc->pos_emb, enc->type_emb, enc->emb_ln_g,
+                                                   enc->emb_ln_b, c.ln_eps, x, seq_len_out);
+    LB2_CUDA_OK(cudaGetLastError());
+    return true;
+}
+
+bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const float* b, __half* out, int rows,
+                      int hidden, float eps) {
+    if (rows <= 0) return true;
+    const int grid = (rows + 7) / 8;
+    if (hidden == 384)
+        layernorm_kernel<12><<<grid, 256, 0, s>>>(in, g, b, out, rows, eps);
+    else if (hidden == 768)
+        layernorm_kernel<24><<<grid, 256, 0, s>>>(in, g, b, out, rows, eps);
+    else {
+        set_error("layernorm: unsupported hidden %d", hidden);
+        return false;
+    }
     LB2_CUDA_OK(cudaGetLastError());
     return true;
 }
@@ -362,26 +409,23 @@ bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_star
     return true;
 }
 
-static bool launch_pool(cudaStream_t s, const Encoder* enc, const __half* y, const float* stats, const float* g,
-                        const float* b, const int32_t* seq_start, int row_base, int n_seq, float* out) {
+bool launch_pool(cudaStream_t s, const __half* x, const int32_t* seq_start, const int32_t* seq_len, int row_base,
+                 int n_seq, int hidden, int pooling, int normalize, float* out) {
     if (n_seq <= 0) return true;
-    const EncoderConfig& c = enc->cfg;
-    if (c.hidden == 384)
-        pool_kernel<3><<<n_seq, 128, 0, s>>>(y, stats, enc->parts, g, b, c.ln_eps, seq_start, enc->seq_len, row_base,
-                                             c.pooling, c.normalize, out);
-    else
-        pool_kernel<6><<<n_seq, 128, 0, s>>>(y, stats, enc->parts, g, b, c.ln_eps, seq_start, enc->seq_len, row_base,
-                                             c.pooling, c.normalize, out);
+    if (hidden == 384)
+        pool_kernel<3><<<n_seq, 128, 0, s>>>(x, seq_start, seq_len, row_base, pooling, normalize, out);
+    else if (hidden == 768)
+        pool_kernel<6><<<n_seq, 128, 0, s>>>(x, seq_start, seq_len, row_base, pooling, normalize, out);
+    else {
+        set_error("pool: unsupported hidden %d", hidden);
+        return false;
+    }
     LB2_CUDA_OK(cudaGetLastError());
     return true;
 }
 
 // ---------------------------------------------------------------------------------------
-// weights: one fp32 host blob (layout documented in include/leann_b200.h) -> fp16/fp32 device arena.
-// Load-time transformations (host, double precision):
-//   * LayerNorm folding for the two GEMMs that consume a normalised tensor (QKV, FFN-up):
-//     W' = fp16(W * gamma), svec[n] = sum_k W'[n,k], tvec[n] = sum_k beta[k] W[n,k] + b[n]   (see EpiArgs);
-//   * QKV rows regrouped per head (q_h | k_h | v_h) so that the GEMM's grouped store is head-major.
+// weights: one fp32 host blob (layout documented in include/leann_b200.h) -> fp16/fp32 device arena
 // ---------------------------------------------------------------------------------------
 size_t encoder_weight_floats(const EncoderConfig& c) {
     const size_t H = c.hidden, F = c.ffn;
@@ -389,30 +433,6 @@ size_t encoder_weight_floats(const EncoderConfig& c) {
     n += (size_t)c.layers * (3 * H * H + 3 * H + H * H + H + 2 * H + F * H + F + H * F + H + 2 * H);
     return n;
 }
-
-namespace {
-struct Folded {
-    std::vector<float> w, s, t;  // W' (fp16-representable values), row sums, folded bias
-};
-Folded fold_layernorm(const float* W, size_t N, size_t K, const float* gamma, const float* beta, const float* bias) {
-    Folded f;
-    f.w.resize(N * K);
-    f.s.resize(N);
-    f.t.resize(N);
-    for (size_t n = 0; n < N; n++) {
-        double s = 0, t = bias[n];
-        for (size_t k = 0; k < K; k++) {
-            const float wp = __half2float(__float2half_rn(W[n * K + k] * gamma[k]));
-            f.w[n * K + k] = wp;
-            s += wp;
-            t += static_cast<double>(beta[k]) * W[n * K + k];
-        }
-        f.s[n] = static_cast<float>(s);
-        f.t[n] = static_cast<float>(t);
-    }
-    return f;
-}
-}  // namespace
 
 bool encoder_load(Encoder* enc, const EncoderConfig& cfg, const float* w, size_t n_floats) {
     if (cfg.hidden != 384 && cfg.hidden != 768) { set_error("encoder: hidden must be 384 or 768 (got %d)", cfg.hidden); return false; }
@@ -429,101 +449,82 @@ bool encoder_load(Encoder* enc, const EncoderConfig& cfg, const float* w, size_t
     }
     encoder_free(enc);
     enc->cfg = cfg;
-    enc->parts = cfg.hidden / 96;
-    const size_t H = cfg.hidden, F = cfg.ffn, Lr = cfg.layers, hd = H / cfg.heads;
-    const size_t h16 = (size_t)cfg.vocab_size * H + (size_t)cfg.max_pos * H + (size_t)cfg.type_vocab * H + Lr * (3 * H * H + H * H + 2 * F * H);
-    const size_t f32 = 2 * H + Lr * (12 * H + 2 * F);
-    const size_t bytes = align_up(h16 * 2, 256) + f32 * 4 + 256 * (24 * Lr + 16);
+    const size_t H = cfg.hidden, F = cfg.ffn, Lr = cfg.layers;
+    // pass 1: sizes
+    size_t h16 = (size_t)cfg.vocab_size * H + (size_t)cfg.max_pos * H + (size_t)cfg.type_vocab * H + Lr * (3 * H * H + H * H + 2 * F * H);
+    size_t f32 = 2 * H + Lr * (3 * H + H + 2 * H + F + H + 2 * H);
+    size_t bytes = align_up(h16 * 2, 256) + f32 * 4 + 256 * (16 * Lr + 16);
     LB2_CUDA_OK(cudaMalloc(&enc->arena, bytes));
     std::vector<__half> hbuf;
     uint8_t* cur = static_cast<uint8_t*>(enc->arena);
-    uint8_t* const end = cur + bytes;
-    auto up16 = [&](const float* src, size_t n) -> __half* {
-        if (cur + align_up(n * 2, 256) > end) return nullptr;
+    const float* src = w;
+    auto put16 = [&](size_t n) -> __half* {
         hbuf.resize(n);
         for (size_t i = 0; i < n; i++) hbuf[i] = __float2half_rn(src[i]);
         __half* dst = reinterpret_cast<__half*>(cur);
         if (cudaMemcpy(dst, hbuf.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
         cur += align_up(n * 2, 256);
+        src += n;
         return dst;
     };
-    auto up32 = [&](const float* src, size_t n) -> float* {
-        if (cur + align_up(n * 4, 256) > end) return nullptr;
+    auto put32 = [&](size_t n) -> float* {
         float* dst = reinterpret_cast<float*>(cur);
         if (cudaMemcpy(dst, src, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
         cur += align_up(n * 4, 256);
+        src += n;
         return dst;
     };
-    const float* word = w;
-    const float* pos = word + (size_t)cfg.vocab_size * H;
-    const float* type = pos + (size_t)cfg.max_pos * H;
-    const float* emb_g = type + (size_t)cfg.type_vocab * H;
-    const float* emb_b = emb_g + H;
-    const float* cursor = emb_b + H;
     bool ok = true;
-    ok &= (enc->word_emb = up16(word, (size_t)cfg.vocab_size * H)) != nullptr;
-    ok &= (enc->pos_emb = up16(pos, (size_t)cfg.max_pos * H)) != nullptr;
-    ok &= (enc->type_emb = up16(type, (size_t)cfg.type_vocab * H)) != nullptr;
-    ok &= (enc->emb_ln_g = up32(emb_g, H)) != nullptr;
-    ok &= (enc->emb_ln_b = up32(emb_b, H)) != nullptr;
+    ok &= (enc->word_emb = put16((size_t)cfg.vocab_size * H)) != nullptr;
+    ok &= (enc->pos_emb = put16((size_t)cfg.max_pos * H)) != nullptr;
+    ok &= (enc->type_emb = put16((size_t)cfg.type_vocab * H)) != nullptr;
+    ok &= (enc->emb_ln_g = put32(H)) != nullptr;
+    ok &= (enc->emb_ln_b = put32(H)) != nullptr;
     enc->layers = new LayerWeights[Lr];
-    const float *prev_g = emb_g, *prev_b = emb_b;  // LayerNorm feeding the current layer's QKV projection
     for (size_t l = 0; l < Lr && ok; l++) {
-        const float* wqkv = cursor;
-        const float* bqkv = wqkv + 3 * H * H;
-        const float* wo = bqkv + 3 * H;
-        const float* bo = wo + H * H;
-        const float* g1 = bo + H;
-        const float* b1ln = g1 + H;
-        const float* w1 = b1ln + H;
-        const float* b1 = w1 + F * H;
-        const float* w2 = b1 + F;
-        const float* b2 = w2 + H * F;
-        const float* g2 = b2 + H;
-        const float* b2ln = g2 + H;
-        cursor = b2ln + H;
         LayerWeights& lw = enc->layers[l];
-        {
-            Folded f = fold_layernorm(wqkv, 3 * H, H, prev_g, prev_b, bqkv);
-            Folded p;  // head-major row order
-            p.w.resize(f.w.size()); p.s.resize(3 * H); p.t.resize(3 * H);
+        {   // rows of [Wq; Wk; Wv] regrouped per head (q_h | k_h | v_h) so that the GEMM output is head-major
+            const size_t hd = H / cfg.heads;
+            std::vector<float> wp(3 * H * H), bp(3 * H);
+            const float* bsrc = src + 3 * H * H;
             for (size_t h = 0; h < (size_t)cfg.heads; h++)
                 for (size_t part = 0; part < 3; part++)
                     for (size_t j = 0; j < hd; j++) {
-                        const size_t dr = h * 3 * hd + part * hd + j, sr = part * H + h * hd + j;
-                        memcpy(&p.w[dr * H], &f.w[sr * H], H * sizeof(float));
-                        p.s[dr] = f.s[sr];
-                        p.t[dr] = f.t[sr];
+                        const size_t dst_row = h * 3 * hd + part * hd + j, src_row = part * H + h * hd + j;
+                        memcpy(&wp[dst_row * H], src + src_row * H, H * sizeof(float));
+                        bp[dst_row] = bsrc[src_row];
                     }
-            ok &= (lw.w_qkv = up16(p.w.data(), 3 * H * H)) != nullptr;
-            ok &= (lw.t_qkv = up32(p.t.data(), 3 * H)) != nullptr;
-            ok &= (lw.s_qkv = up32(p.s.data(), 3 * H)) != nullptr;
+            const float* keep = src;
+            src = wp.data();
+            ok &= (lw.w_qkv = put16(3 * H * H)) != nullptr;
+            src = bp.data();
+            ok &= (lw.b_qkv = put32(3 * H)) != nullptr;
+            src = keep + 3 * H * H + 3 * H;
         }
-        ok &= (lw.w_o = up16(wo, H * H)) != nullptr;
-        ok &= (lw.b_o = up32(bo, H)) != nullptr;
-        ok &= (lw.ln1_g = up32(g1, H)) != nullptr;
-        ok &= (lw.ln1_b = up32(b1ln, H)) != nullptr;
-        {
-            Folded f = fold_layernorm(w1, F, H, g1, b1ln, b1);
-            ok &= (lw.w_1 = up16(f.w.data(), F * H)) != nullptr;
-            ok &= (lw.t_1 = up32(f.t.data(), F)) != nullptr;
-            ok &= (lw.s_1 = up32(f.s.data(), F)) != nullptr;
-        }
-        ok &= (lw.w_2 = up16(w2, H * F)) != nullptr;
-        ok &= (lw.b_2 = up32(b2, H)) != nullptr;
-        ok &= (lw.ln2_g = up32(g2, H)) != nullptr;
-        ok &= (lw.ln2_b = up32(b2ln, H)) != nullptr;
+        ok &= (lw.w_o = put16(H * H)) != nullptr;
+        ok &= (lw.b_o = put32(H)) != nullptr;
+        ok &= (lw.ln1_g = put32(H)) != nullptr;
+        ok &= (lw.ln1_b = put32(H)) != nullptr;
+        ok &= (lw.w_1 = put16(F * H)) != nullptr;
+        ok &= (lw.b_1 = put32(F)) != nullptr;
+        ok &= (lw.w_2 = put16(H * F)) != nullptr;
+        ok &= (lw.b_2 = put32(H)) != nullptr;
+        ok &= (lw.ln2_g = put32(H)) != nullptr;
+        ok &= (lw.ln2_b = put32(H)) != nullptr;
         if (!ok) break;
         const uint32_t bn = gemm_block_n();
         ok &= make_tmap_f16_2d(&lw.tm_qkv, lw.w_qkv, 3 * H, H, bn);
         ok &= make_tmap_f16_2d(&lw.tm_o, lw.w_o, H, H, bn);
         ok &= make_tmap_f16_2d(&lw.tm_1, lw.w_1, F, H, bn);
         ok &= make_tmap_f16_2d(&lw.tm_2, lw.w_2, H, F, bn);
-        prev_g = g2;
-        prev_b = b2ln;
     }
     if (!ok) {
-        set_error("encoder: uploading the weights failed (arena %zu bytes)", bytes);
+        if (cur > static_cast<uint8_t*>(enc->arena) + bytes) set_error("encoder: arena overflow");
+        encoder_free(enc);
+        return false;
+    }
+    if (static_cast<size_t>(cur - static_cast<uint8_t*>(enc->arena)) > bytes) {
+        set_error("encoder: arena overflow");
         encoder_free(enc);
         return false;
     }
@@ -534,29 +535,18 @@ bool encoder_load(Encoder* enc, const EncoderConfig& cfg, const float* w, size_t
     return true;
 }
 
-static void free_workspaces(Encoder* enc) {
-    for (int i = 0; i < 3; i++) {
-        if (enc->p[i]) cudaFree(enc->p[i]);
-        if (enc->st[i]) cudaFree(enc->st[i]);
-        enc->p[i] = nullptr;
-        enc->st[i] = nullptr;
-    }
-    for (__half** q : {&enc->qkv, &enc->ctx, &enc->ffn}) {
-        if (*q) cudaFree(*q);
-        *q = nullptr;
-    }
-    enc->cap_tokens = 0;
-}
-
 void encoder_free(Encoder* enc) {
     if (enc->arena) cudaFree(enc->arena);
     enc->arena = nullptr;
     delete[] enc->layers;
     enc->layers = nullptr;
-    free_workspaces(enc);
+    for (__half** p : {&enc->x, &enc->y, &enc->qkv, &enc->ctx, &enc->ffn}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
     if (enc->seq_len) cudaFree(enc->seq_len);
     enc->seq_len = nullptr;
-    enc->cap_seqs = 0;
+    enc->cap_tokens = enc->cap_seqs = 0;
     enc->loaded = false;
 }
 
@@ -569,12 +559,14 @@ bool encoder_reserve(Encoder* enc, int64_t tokens, int64_t seqs) {
         enc->cap_seqs = seqs;
     }
     if (tokens <= enc->cap_tokens) return true;
-    free_workspaces(enc);
-    const size_t H = enc->cfg.hidden, F = enc->cfg.ffn, T = static_cast<size_t>(tokens);
-    for (int i = 0; i < 3; i++) {
-        LB2_CUDA_OK(cudaMalloc(&enc->p[i], T * H * 2));
-        LB2_CUDA_OK(cudaMalloc(&enc->st[i], T * 2 * enc->parts * sizeof(float)));
+    for (__half** p : {&enc->x, &enc->y, &enc->qkv, &enc->ctx, &enc->ffn}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
     }
+    enc->cap_tokens = 0;
+    const size_t H = enc->cfg.hidden, F = enc->cfg.ffn, T = static_cast<size_t>(tokens);
+    LB2_CUDA_OK(cudaMalloc(&enc->x, T * H * 2));
+    LB2_CUDA_OK(cudaMalloc(&enc->y, T * H * 2));
     LB2_CUDA_OK(cudaMalloc(&enc->qkv, T * 3 * H * 2));
     LB2_CUDA_OK(cudaMalloc(&enc->ctx, T * H * 2));
     LB2_CUDA_OK(cudaMalloc(&enc->ffn, T * F * 2));
@@ -594,49 +586,31 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
     }
     const EncoderConfig& c = enc->cfg;
     const int H = c.hidden, F = c.ffn, T = n_tokens, sms = enc->num_sms;
-    const float inv_w = 1.0f / static_cast<float>(H);
-    auto gemm = [&](const __half* A, const CUtensorMap* tm, const __half* W, const EpiArgs& ea, const __half* res,
+    if (!launch_embed_ln(st, enc, tok_store, tok_off, seq_node, seq_start, row_base, n_seq, enc->x, enc->seq_len)) return false;
+    auto gemm = [&](const __half* A, const CUtensorMap* tm, const __half* W, const float* bias, const __half* res,
                     __half* C, int N, int K, int epi, int c_group = 0) {
         prof_begin(st, PROF_GEMM);
-        const bool ok = gemm_f16(st, A, tm, W, ea, res, C, T, N, K, epi, sms, c_group);
+        const bool ok = gemm_f16(st, A, tm, W, bias, res, C, T, N, K, epi, sms, c_group);
         prof_end(st, PROF_GEMM, 2.0 * T * (double)N * K);
         return ok;
     };
-    prof_begin(st, PROF_NORM);
-    if (!launch_embed(st, enc, tok_store, tok_off, seq_node, seq_start, row_base, n_seq, enc->p[0], enc->st[0])) return false;
-    prof_end(st, PROF_NORM, 0);
-    int a = 0;                                                  // p[a] / st[a]: pre-LN input of the layer
-    const float *in_g = enc->emb_ln_g, *in_b = enc->emb_ln_b;  // ... and the LayerNorm that applies to it
     for (int l = 0; l < c.layers; l++) {
         const LayerWeights& w = enc->layers[l];
-        const int b = (a + 1) % 3, cidx = (a + 2) % 3;
-        EpiArgs e_qkv;  // qkv = LN_in(p[a]) Wqkv^T + b   (LN folded: see EpiArgs)
-        e_qkv.bias = w.t_qkv; e_qkv.svec = w.s_qkv; e_qkv.stats_in = enc->st[a]; e_qkv.parts_in = enc->parts;
-        e_qkv.inv_width = inv_w; e_qkv.eps = c.ln_eps;
-        if (!gemm(enc->p[a], &w.tm_qkv, w.w_qkv, e_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS, 3 * (H / c.heads))) return false;
+        if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS, 3 * (H / c.heads))) return false;
         prof_begin(st, PROF_ATTN);
         if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, row_base, c.max_pos, n_seq, T, H, c.heads, enc->ctx)) return false;
         prof_end(st, PROF_ATTN, 0);
-        EpiArgs e_o;  // p[b] = ctx Wo^T + bo + LN_in(p[a]);  emits the row statistics of p[b]
-        e_o.bias = w.b_o; e_o.stats_in = enc->st[a]; e_o.parts_in = enc->parts; e_o.ln_g = in_g; e_o.ln_b = in_b;
-        e_o.stats_out = enc->st[b]; e_o.inv_width = inv_w; e_o.eps = c.ln_eps;
-        if (!gemm(enc->ctx, &w.tm_o, w.w_o, e_o, enc->p[a], enc->p[b], H, H, EPI_BIAS_RES)) return false;
-        EpiArgs e_1;  // ffn = gelu(LN1(p[b]) W1^T + b1)
-        e_1.bias = w.t_1; e_1.svec = w.s_1; e_1.stats_in = enc->st[b]; e_1.parts_in = enc->parts;
-        e_1.inv_width = inv_w; e_1.eps = c.ln_eps;
-        if (!gemm(enc->p[b], &w.tm_1, w.w_1, e_1, nullptr, enc->ffn, F, H, EPI_BIAS_GELU)) return false;
-        EpiArgs e_2;  // p[c] = ffn W2^T + b2 + LN1(p[b]);  emits the row statistics of p[c]
-        e_2.bias = w.b_2; e_2.stats_in = enc->st[b]; e_2.parts_in = enc->parts; e_2.ln_g = w.ln1_g; e_2.ln_b = w.ln1_b;
-        e_2.stats_out = enc->st[cidx]; e_2.inv_width = inv_w; e_2.eps = c.ln_eps;
-        if (!gemm(enc->ffn, &w.tm_2, w.w_2, e_2, enc->p[b], enc->p[cidx], H, F, EPI_BIAS_RES)) return false;
-        a = cidx;
-        in_g = w.ln2_g;
-        in_b = w.ln2_b;
+        if (!gemm(enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, enc->y, H, H, EPI_BIAS_RES)) return false;
+        prof_begin(st, PROF_NORM);
+        if (!launch_layernorm(st, enc->y, w.ln1_g, w.ln1_b, enc->x, T, H, c.ln_eps)) return false;
+        prof_end(st, PROF_NORM, 0);
+        if (!gemm(enc->x, &w.tm_1, w.w_1, w.b_1, nullptr, enc->ffn, F, H, EPI_BIAS_GELU)) return false;
+        if (!gemm(enc->ffn, &w.tm_2, w.w_2, w.b_2, enc->x, enc->y, H, F, EPI_BIAS_RES)) return false;
+        prof_begin(st, PROF_NORM);
+        if (!launch_layernorm(st, enc->y, w.ln2_g, w.ln2_b, enc->x, T, H, c.ln_eps)) return false;
+        prof_end(st, PROF_NORM, 0);
     }
-    prof_begin(st, PROF_NORM);
-    const bool ok = launch_pool(st, enc, enc->p[a], enc->st[a], in_g, in_b, seq_start, row_base, n_seq, out);
-    prof_end(st, PROF_NORM, 0);
-    return ok;
+    return launch_pool(st, enc->x, seq_start, enc->seq_len, row_base, n_seq, H, c.pooling, c.normalize, out);
 }
 
 }  // namespace lb2

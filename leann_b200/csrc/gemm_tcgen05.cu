@@ -59,11 +59,11 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
-template <int BLOCK_N, int STAGES, int EPI, bool LN>
+template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                   const EpiArgs ea, int M, int N, int K, int c_group) {
+                   const float* __restrict__ bias, int M, int N, int K, int c_group) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                             : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -182,24 +182,6 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t aphase = (it >> 1) & 1;
             const int row0 = m_blk * BLOCK_M + quarter * 32;
             const int colbase = n_blk * BLOCK_N + half * NCH * 32;
-            // deferred LayerNorm: this thread's row statistics (fixed-order sum of the producer's partials)
-            float ln_r = 1.f, ln_nmr = 0.f;  // r and -mu * r
-            if (LN) {
-                const int grow = row0 + lane;
-                if (grow < M) {
-                    const float2* sp = reinterpret_cast<const float2*>(ea.stats_in) + static_cast<size_t>(grow) * ea.parts_in;
-                    float ssum = 0.f, ssq = 0.f;
-                    for (int pi = 0; pi < ea.parts_in; pi++) {
-                        const float2 pv = __ldg(sp + pi);
-                        ssum += pv.x;
-                        ssq += pv.y;
-                    }
-                    const float mu = ssum * ea.inv_width;
-                    ln_r = rsqrtf(fmaxf(ssq * ea.inv_width - mu * mu, 0.f) + ea.eps);
-                    ln_nmr = -mu * ln_r;
-                }
-            }
-            float st_sum = 0.f, st_sq = 0.f;  // partial stats of the row this thread writes (EPI_BIAS_RES)
             if (EPI == EPI_BIAS_RES) {
                 if (lane == 0) {
                     ptx::bulk_wait_read<0>();  // previous tile's stores no longer read the boxes
@@ -230,12 +212,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (lane == 0) ptx::bulk_wait_read<NCH - 1>();
                     __syncwarp();
                 }
-                const float4* bp = reinterpret_cast<const float4*>(ea.bias + col0);
-                constexpr bool ln_in = LN && (EPI != EPI_BIAS_RES);
-                constexpr bool ln_res = LN && (EPI == EPI_BIAS_RES);
-                const float4* sp4 = reinterpret_cast<const float4*>((ln_in ? ea.svec : ea.bias) + col0);
-                const float4* gp4 = reinterpret_cast<const float4*>((ln_res ? ea.ln_g : ea.bias) + col0);
-                const float4* lb4 = reinterpret_cast<const float4*>((ln_res ? ea.ln_b : ea.bias) + col0);
+                const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) {  // 16-byte piece j4 of this thread's 64-byte row segment
                     uint4* slot = reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4));
@@ -243,17 +220,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const float4 b4 = __ldg(bp + 2 * j4 + u);  // warp-uniform address: one broadcast transaction
-                        float a0 = __uint_as_float(acc[8 * j4 + 4 * u + 0]), a1 = __uint_as_float(acc[8 * j4 + 4 * u + 1]);
-                        float a2 = __uint_as_float(acc[8 * j4 + 4 * u + 2]), a3 = __uint_as_float(acc[8 * j4 + 4 * u + 3]);
-                        if (ln_in) {  // r * (acc - mu * s) + t = r * acc + ((-mu r) * s + t): two FMAs per element
-                            const float4 s4 = __ldg(sp4 + 2 * j4 + u);
-                            v[4 * u + 0] = fmaf(ln_r, a0, fmaf(ln_nmr, s4.x, b4.x));
-                            v[4 * u + 1] = fmaf(ln_r, a1, fmaf(ln_nmr, s4.y, b4.y));
-                            v[4 * u + 2] = fmaf(ln_r, a2, fmaf(ln_nmr, s4.z, b4.z));
-                            v[4 * u + 3] = fmaf(ln_r, a3, fmaf(ln_nmr, s4.w, b4.w));
-                        } else {
-                            v[4 * u + 0] = a0 + b4.x; v[4 * u + 1] = a1 + b4.y; v[4 * u + 2] = a2 + b4.z; v[4 * u + 3] = a3 + b4.w;
-                        }
+                        v[4 * u + 0] = __uint_as_float(acc[8 * j4 + 4 * u + 0]) + b4.x;
+                        v[4 * u + 1] = __uint_as_float(acc[8 * j4 + 4 * u + 1]) + b4.y;
+                        v[4 * u + 2] = __uint_as_float(acc[8 * j4 + 4 * u + 2]) + b4.z;
+                        v[4 * u + 3] = __uint_as_float(acc[8 * j4 + 4 * u + 3]) + b4.w;
                     }
                     if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
@@ -262,40 +232,17 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (EPI == EPI_BIAS_RES) {
                         const uint4 rv = *slot;
                         const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-                        float rf[8];
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            const float2 t2 = __half22float2(rh[u]);
-                            rf[2 * u] = t2.x;
-                            rf[2 * u + 1] = t2.y;
+                            const float2 rf = __half22float2(rh[u]);
+                            v[2 * u] += rf.x;
+                            v[2 * u + 1] += rf.y;
                         }
-                        if (ln_res) {  // residual = LayerNorm(p) = (p * r - mu r) * gamma + beta
-#pragma unroll
-                            for (int u = 0; u < 2; u++) {
-                                const float4 g4 = __ldg(gp4 + 2 * j4 + u), e4 = __ldg(lb4 + 2 * j4 + u);
-                                rf[4 * u + 0] = fmaf(fmaf(rf[4 * u + 0], ln_r, ln_nmr), g4.x, e4.x);
-                                rf[4 * u + 1] = fmaf(fmaf(rf[4 * u + 1], ln_r, ln_nmr), g4.y, e4.y);
-                                rf[4 * u + 2] = fmaf(fmaf(rf[4 * u + 2], ln_r, ln_nmr), g4.z, e4.z);
-                                rf[4 * u + 3] = fmaf(fmaf(rf[4 * u + 3], ln_r, ln_nmr), g4.w, e4.w);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) v[u] += rf[u];
                     }
                     uint4 ov;
                     __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
                     for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
-                    if (EPI == EPI_BIAS_RES) {
-                        if (LN) {  // statistics of the values actually stored (fp16-rounded)
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const float2 t2 = __half22float2(oh[u]);
-                                st_sum += t2.x + t2.y;
-                                st_sq = fmaf(t2.x, t2.x, fmaf(t2.y, t2.y, st_sq));
-                            }
-                        }
-                    }
                     *slot = ov;
                 }
                 ptx::fence_async_smem();
@@ -306,14 +253,6 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     else
                         ptx::tma_store_2d(&tmap_c, stage_buf + c * 2048, col0, row0);
                     ptx::bulk_commit();
-                }
-            }
-            if (EPI == EPI_BIAS_RES) {
-                if (LN && ea.stats_out != nullptr && row0 + lane < M) {
-                    // slot = which 96-column slice of the row this warp covered
-                    const int parts_out = N / (NCH * 32);
-                    float2* so = reinterpret_cast<float2*>(ea.stats_out) + static_cast<size_t>(row0 + lane) * parts_out;
-                    so[n_blk * 2 + half] = make_float2(st_sum, st_sq);
                 }
             }
             ptx::tc_fence_before();
@@ -398,11 +337,11 @@ static bool make_tmap_f16_grouped(CUtensorMap* map, const void* ptr, uint64_t ro
 constexpr int GEMM_BLOCK_N = 192;
 constexpr int GEMM_STAGES = 4;
 
-template <int EPI, bool LN>
+template <int EPI>
 static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                               const CUtensorMap& tr, const EpiArgs& ea, int M, int N, int K, int c_group, int num_sms) {
+                               const CUtensorMap& tr, const float* bias, int M, int N, int K, int c_group, int num_sms) {
     using L = GemmSmem<GEMM_BLOCK_N, GEMM_STAGES>;
-    auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI, LN>;
+    auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -411,22 +350,17 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, ea, M, N, K, c_group);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group);
     return cudaGetLastError();
 }
 
 // A [M,K] fp16 row-major, W [N,K] fp16 row-major (nn.Linear layout), C [M,N] fp16.
 // c_group > 0: C is written group-major, [N / c_group][M][c_group] (the per-head q|k|v layout attention reads).
-bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const EpiArgs& ea,
+bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms, int c_group) {
     if (M <= 0) return true;
     if (N % GEMM_BLOCK_N != 0 || K % BLOCK_K != 0) {
         set_error("gemm_f16: unsupported shape N=%d K=%d (need N%%192==0, K%%64==0)", N, K);
-        return false;
-    }
-    if (!ea.bias || (ea.stats_in && ea.parts_in <= 0) || (ea.stats_in && epi != EPI_BIAS_RES && !ea.svec) ||
-        (ea.ln_g && (!ea.ln_b || !ea.stats_in))) {
-        set_error("gemm_f16: inconsistent epilogue arguments");
         return false;
     }
     if (epi == EPI_BIAS_RES && !residual) {
@@ -450,20 +384,12 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
         tmap_w = &tb_local;
     }
     cudaError_t e;
-    const bool ln = ea.stats_in != nullptr;  // deferred-LayerNorm epilogue (LN-in for epilogues 0/1, LN-res for 2)
-    if (ln && epi == EPI_BIAS_RES && (!ea.ln_g || !ea.stats_out)) {
-        set_error("gemm_f16: LN-res epilogue needs ln_g / ln_b / stats_out");
-        return false;
-    }
-#define LB2_LAUNCH(E) (ln ? launch_gemm<E, true>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms) \
-                          : launch_gemm<E, false>(stream, ta, *tmap_w, tc, tr, ea, M, N, K, c_group, num_sms))
     switch (epi) {
-        case EPI_BIAS: e = LB2_LAUNCH(EPI_BIAS); break;
-        case EPI_BIAS_GELU: e = LB2_LAUNCH(EPI_BIAS_GELU); break;
-        case EPI_BIAS_RES: e = LB2_LAUNCH(EPI_BIAS_RES); break;
+        case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
+        case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
+        case EPI_BIAS_RES: e = launch_gemm<EPI_BIAS_RES>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
         default: set_error("gemm_f16: bad epilogue %d", epi); return false;
     }
-#undef LB2_LAUNCH
     if (e != cudaSuccess) {
         set_error("gemm_f16 launch: %s", cudaGetErrorString(e));
         return false;
