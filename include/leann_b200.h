@@ -142,6 +142,12 @@ int lb2_encode_range_device(lb2_index* idx, int64_t first, int64_t n, float* d_o
 /* Tunables (0 keeps the current value): traversal slots in flight, passages per encoder pass. */
 int lb2_configure(lb2_index* idx, int32_t slots, int32_t passages_per_pass);
 
+/* Generic knobs: "slots", "passages_per_pass", "profile" (0/1: per-kernel-class CUDA-event timing in the stats),
+ * "dedup_scope": 0 (default) = a passage requested by several queries in the same hop is encoded once;
+ * 1 = once per search call (later hops of any query in the call reuse the embedding; one fp32 row per distinct
+ * passage lives in HBM until the call returns — identical results, fewer recomputes, nothing persists). */
+int lb2_set_option(lb2_index* idx, const char* key, int64_t value);
+
 /* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
 int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);

@@ -111,6 +111,8 @@ class B200HnswSearcher(LeannBackendSearcherInterface):
         self.preset: synth.ModelPreset | None = None
         if kwargs.get("slots") or kwargs.get("passages_per_pass"):
             self._index.configure(int(kwargs.get("slots", 0)), int(kwargs.get("passages_per_pass", 0)))
+        if kwargs.get("dedup_scope") is not None:  # "hop" (default) | "call"
+            self._index.set_option("dedup_scope", {"hop": 0, "call": 1}[str(kwargs["dedup_scope"])])
 
     # ------------------------------------------------------------------ helpers
     def _load_meta(self) -> dict[str, Any]:

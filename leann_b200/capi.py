@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "lb2_last_error", "lb2_version", "lb2_open", "lb2_close", "lb2_info", "lb2_set_vectors", "lb2_set_passages",
     "lb2_encoder_weight_count", "lb2_set_encoder", "lb2_default_params", "lb2_search", "lb2_search_device",
     "lb2_last_query_stats", "lb2_encode_ids", "lb2_encode_tokens", "lb2_encode_range_device", "lb2_configure",
+    "lb2_set_option",
     "lb2_test_gemm_f16", "lb2_test_gemm_grouped_f16", "lb2_test_layernorm_f16", "lb2_test_attention_f16",
 ]
 
@@ -86,6 +87,7 @@ def load():
     lib.lb2_encode_tokens.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lb2_encode_range_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.lb2_configure.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.lb2_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.lb2_test_gemm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int]
     lib.lb2_test_layernorm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
@@ -166,6 +168,9 @@ class Index:
 
     def configure(self, slots: int = 0, passages_per_pass: int = 0):
         _check(self._lib.lb2_configure(self._h, int(slots), int(passages_per_pass)), "lb2_configure")
+
+    def set_option(self, key: str, value: int):
+        _check(self._lib.lb2_set_option(self._h, key.encode(), int(value)), f"lb2_set_option({key})")
 
     def search(self, q: np.ndarray, k: int, params: SearchParams | None = None):
         q = np.ascontiguousarray(q, np.float32)

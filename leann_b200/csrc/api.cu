@@ -131,6 +131,7 @@ struct lb2_index {
     // tunables
     int cfg_slots = 0;
     int per_pass = 4096;
+    int dedup_call_scope = 0;  // 0: de-duplicate recomputes per hop (default), 1: per search call
     // traversal state
     TravState st{};
     TravParams alloc_p{};
@@ -138,6 +139,7 @@ struct lb2_index {
     int64_t alloc_nq = 0;
     bool alloc_recompute = false;
     int cap_unique = 0;
+    int64_t cap_E_rows = 0;
     float* d_E = nullptr;
     HopCtrl* h_ctrl = nullptr;  // pinned + mapped
     int* h_bounds = nullptr;    // pinned + mapped
@@ -191,12 +193,15 @@ void free_state(lb2_index* x) {
     x->h_ctrl = nullptr; x->h_bounds = nullptr;
     x->alloc_S = 0;
     x->cap_unique = 0;
+    x->cap_E_rows = 0;
 }
 
 bool ensure_state(lb2_index* x, int S, const TravParams& p, bool recompute) {
     const TravParams& a = x->alloc_p;
+    const int64_t need_rows = !recompute ? 0 : (x->dedup_call_scope ? std::max<int64_t>(x->g.ntotal, (int64_t)S * p.cap_req) : (int64_t)S * p.cap_req);
     // strides depend on S / hcap / k / cap_req: reallocate on any change (calls with stable params reuse)
-    if (x->alloc_S == S && a.hcap == p.hcap && a.k == p.k && a.cap_req == p.cap_req && (!recompute || x->alloc_recompute))
+    if (x->alloc_S == S && a.hcap == p.hcap && a.k == p.k && a.cap_req == p.cap_req && (!recompute || x->alloc_recompute) &&
+        x->cap_E_rows >= need_rows)
         return true;
     free_state(x);
     TravState& s = x->st;
@@ -224,7 +229,8 @@ bool ensure_state(lb2_index* x, int S, const TravParams& p, bool recompute) {
         x->max_chunks = (x->cap_unique + x->per_pass - 1) / x->per_pass + 1;
         ok = dev_alloc(&s.stamp, (size_t)N) && dev_alloc(&s.slot_of[0], (size_t)N) && dev_alloc(&s.slot_of[1], (size_t)N) &&
              dev_alloc(&s.claim, 1) && dev_alloc(&s.uniq_node, (size_t)x->cap_unique) &&
-             dev_alloc(&s.seq_start, (size_t)x->cap_unique) && dev_alloc(&x->d_E, (size_t)x->cap_unique * x->g.d);
+             dev_alloc(&s.seq_start, (size_t)x->cap_unique) && dev_alloc(&x->d_E, (size_t)need_rows * x->g.d);
+        x->cap_E_rows = ok ? need_rows : 0;
         if (ok && cudaMemsetAsync(s.stamp, 0, (size_t)N * 4, x->stream) != cudaSuccess) ok = false;
         if (ok && cudaHostAlloc(reinterpret_cast<void**>(&x->h_ctrl), sizeof(HopCtrl), cudaHostAllocMapped) != cudaSuccess) ok = false;
         if (ok && cudaHostAlloc(reinterpret_cast<void**>(&x->h_bounds), sizeof(int) * (x->max_chunks + 2), cudaHostAllocMapped) != cudaSuccess) ok = false;
@@ -329,9 +335,14 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
         if (!launch_step(st, x->g, tp, s, 1 << 30, x->num_sms)) return LB2_ERR_CUDA;
         launches++; steps++;
     } else {
+        s.call_scope = x->dedup_call_scope;
+        const uint32_t call_epoch = x->epoch + 1;  // > every stamp written so far
+        int64_t rows_this_call = 0;
         for (;;) {
             x->epoch++;
             s.epoch = x->epoch;
+            s.stamp_value = s.call_scope ? call_epoch : s.epoch;
+            s.row_base_hop = s.call_scope ? (int)rows_this_call : 0;
             cudaMemsetAsync(s.claim, 0, sizeof(unsigned long long), st);
             if (!launch_step(st, x->g, tp, s, 1, x->num_sms)) return LB2_ERR_CUDA;
             gather_bounds_kernel<<<1, 64, 0, st>>>(s.claim, s.n_done, s.seq_start, x->per_pass, x->h_ctrl, x->h_bounds, x->max_chunks);
@@ -340,7 +351,10 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
             if (e != cudaSuccess) { set_error("traversal step failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
             const HopCtrl c = *x->h_ctrl;
             if (c.n_unique == 0) break;  // every slot idle: all queries done
-            if (c.n_unique > x->cap_unique) { set_error("internal: hop work list overflow"); return LB2_ERR_CUDA; }
+            if (c.n_unique > x->cap_unique || s.row_base_hop + (int64_t)c.n_unique > x->cap_E_rows) {
+                set_error("internal: hop work list overflow");
+                return LB2_ERR_CUDA;
+            }
             n_recomputed += c.n_unique;
             n_tokens += c.n_tokens;
             cudaEventRecord(x->ev_enc.get(), st);
@@ -350,11 +364,12 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
                 const int row_base = x->h_bounds[ch];
                 const int n_tok = x->h_bounds[ch + 1] - row_base;
                 if (!encoder_forward(&x->enc, st, x->d_tokens, x->d_tok_off, s.uniq_node + first, s.seq_start + first,
-                                     row_base, n_seq, n_tok, x->d_E + (size_t)first * x->g.d))
+                                     row_base, n_seq, n_tok, x->d_E + ((size_t)s.row_base_hop + first) * x->g.d))
                     return LB2_ERR_CUDA;
                 launches += encoder_kernels_per_pass(x->enc);
             }
             cudaEventRecord(x->ev_enc.get(), st);
+            rows_this_call += c.n_unique;
             if (x->ev_enc.used > 4000 || g_prof_pool[PROF_GEMM].used > 8000) {
                 cudaStreamSynchronize(st);
                 x->ev_enc.drain();
@@ -568,6 +583,20 @@ int lb2_configure(lb2_index* x, int32_t slots, int32_t per_pass) {
         x->cap_enc = 0;
     }
     return LB2_OK;
+}
+
+int lb2_set_option(lb2_index* x, const char* key, int64_t value) {
+    if (!x || !key) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (!strcmp(key, "slots")) return lb2_configure(x, (int32_t)value, 0);
+    if (!strcmp(key, "passages_per_pass")) return lb2_configure(x, 0, (int32_t)value);
+    if (!strcmp(key, "dedup_scope")) {  // 0 = per hop, 1 = per search call
+        if (value != 0 && value != 1) { set_error("dedup_scope must be 0 (hop) or 1 (call)"); return LB2_ERR_ARG; }
+        x->dedup_call_scope = (int)value;
+        return LB2_OK;
+    }
+    if (!strcmp(key, "profile")) { x->profile_gemm = value != 0; return LB2_OK; }
+    set_error("unknown option '%s'", key);
+    return LB2_ERR_ARG;
 }
 
 int lb2_search_device(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,

@@ -232,8 +232,11 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
         for (int j = lane; j < d; j += 32) w.q[j] = qg[j];
     }
     __syncwarp();
-    const int* slot_rd = st.slot_of[(st.epoch + 1) & 1];  // written by the previous hop
-    int* slot_wr = st.slot_of[st.epoch & 1];
+    // hop scope: rows are per hop, so the table is double-buffered by hop parity (this launch reads what the
+    // previous launch wrote while claiming new rows); call scope: a node's row is assigned once per call and
+    // only read by later launches, so one table serves both.
+    const int* slot_rd = st.call_scope ? st.slot_of[0] : st.slot_of[(st.epoch + 1) & 1];
+    int* slot_wr = st.call_scope ? st.slot_of[0] : st.slot_of[st.epoch & 1];
     bool have_pending = (phase != PH_FETCH) && (n_req > 0);
 
     for (int iter = 0; iter < max_iters; iter++) {
@@ -434,8 +437,8 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
             // claim a row of the hop's unique work list for every node nobody requested yet this hop
             for (int i = lane; i < n_req; i += 32) {
                 const int node = w.rq[i];
-                const uint32_t old = atomicMax(&st.stamp[node], st.epoch);
-                if (old < st.epoch) {
+                const uint32_t old = atomicMax(&st.stamp[node], st.stamp_value);
+                if (old < st.stamp_value) {
                     int len = static_cast<int>(st.tok_off[node + 1] - st.tok_off[node]);
                     len = len < st.max_pos ? len : st.max_pos;
                     const unsigned long long packed =
@@ -443,7 +446,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                     const int us = static_cast<int>(packed >> 40);
                     st.uniq_node[us] = node;
                     st.seq_start[us] = static_cast<int>(packed & ((1ull << 40) - 1));
-                    slot_wr[node] = us;
+                    slot_wr[node] = st.row_base_hop + us;
                 }
             }
             have_pending = false;  // distances arrive with the next launch

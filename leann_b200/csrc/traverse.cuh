@@ -64,6 +64,13 @@ struct TravState {
     const uint64_t* tok_off;    // [ntotal+1] passage token offsets
     int max_pos;
     uint32_t epoch;             // hop counter (>= 1)
+    // de-duplication scope of the recompute work list:
+    //   hop  (call_scope = 0): a node requested by several queries in the SAME hop is encoded once;
+    //   call (call_scope = 1): ... once per search call — later hops of any query reuse the row (E keeps
+    //        one row per distinct node for the duration of the call; nothing persists across calls).
+    int call_scope;
+    uint32_t stamp_value;       // value written to stamp[]: hop epoch (hop scope) or call epoch (call scope)
+    int row_base_hop;           // first E row of this hop's new nodes (0 in hop scope)
 };
 
 size_t step_smem_bytes(const TravParams& p, int d, int warps);

@@ -157,6 +157,28 @@ def test_recompute_search_is_exact_given_the_gpu_embeddings(lib, cuda_ok, rc, ca
     assert st.n_recomputed < st.n_requested  # cross-query de-duplication happened (shared entry point at least)
 
 
+def test_call_scope_dedup_gives_identical_results_with_fewer_recomputes(lib, cuda_ok, rc):
+    idx = capi.Index(str(rc["dir"] / "rc.index"))
+    idx.set_passages(rc["corpus"].tokens, rc["corpus"].offsets)
+    idx.set_encoder(rc["preset"].config(), rc["blob"])
+    idx.configure(slots=16, passages_per_pass=512)
+    p = capi.make_params(48, 2, recompute=True)
+    D0, I0 = idx.search(rc["Q"], 10, p)
+    n_hop = idx.last_stats.n_recomputed
+    idx.set_option("dedup_scope", 1)
+    D1, I1 = idx.search(rc["Q"], 10, p)
+    n_call = idx.last_stats.n_recomputed
+    D2, I2 = idx.search(rc["Q"], 10, p)  # a second call starts from an empty table again
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1) and np.array_equal(I1, I2) and np.array_equal(D1, D2)
+    assert n_call < n_hop and idx.last_stats.n_recomputed == n_call
+    assert n_call <= rc["corpus"].n  # at most one encode per distinct passage per call
+    idx.set_option("dedup_scope", 0)
+    D3, I3 = idx.search(rc["Q"], 10, p)
+    assert np.array_equal(I0, I3) and idx.last_stats.n_recomputed == n_hop
+    with pytest.raises(capi.Lb2Error, match="unknown option"):
+        idx.set_option("nope", 1)
+
+
 def test_recompute_vs_fp32_reference_pipeline(lib, cuda_ok, rc):
     """Tier B: oracle traversal whose distances_batch is the fp32 BertModel forward
     (the reference's whole path on CPU) vs the GPU path: same ids where the gaps exceed fp16 noise,
