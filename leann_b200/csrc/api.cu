@@ -253,7 +253,7 @@ int next_pow2(int v) {
     return p;
 }
 
-int encoder_kernels_per_pass(const Encoder& e) { return 2 + e.cfg.layers * 7; }
+int encoder_kernels_per_pass(const Encoder& e) { return 3 + e.cfg.layers * 7; }  // embed, work list, pool + 7 per layer
 
 int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
                 const lb2_search_params* prm, lb2_search_stats* stats) {
@@ -707,7 +707,14 @@ int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, vo
 
 int lb2_test_attention_f16(const void* dqkv, const int32_t* d_seq_start, const int32_t* d_seq_len, int n_seq, int n_tokens,
                            int hidden, int heads, int max_len, void* dctx) {
-    const bool ok = launch_attention(0, (const __half*)dqkv, d_seq_start, d_seq_len, 0, max_len, n_seq, n_tokens, hidden, heads, (__half*)dctx);
+    static int* items = nullptr;  // scratch of the hook: grows, never shrinks
+    static int cap = 0;
+    if (n_seq > cap) {
+        if (!dev_alloc(&items, (size_t)n_seq * 8 + 1)) { cap = 0; return LB2_ERR_CUDA; }
+        cap = n_seq;
+    }
+    const bool ok = launch_attention(0, (const __half*)dqkv, d_seq_start, d_seq_len, items, items + (size_t)cap * 8, 0, max_len,
+                                     n_seq, n_tokens, hidden, heads, (__half*)dctx, true);
     cudaError_t e = cudaDeviceSynchronize();
     if (!ok) return LB2_ERR_CUDA;
     if (e != cudaSuccess) { set_error("attention: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }

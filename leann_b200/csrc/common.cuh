@@ -66,6 +66,7 @@ struct Encoder {
     int64_t cap_tokens = 0, cap_seqs = 0;
     __half *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
     int32_t* seq_len = nullptr;  // [cap_seqs] truncated passage lengths of the current pass
+    int* att_items = nullptr;    // [cap_seqs * 8 + 1] attention work list of the pass + its length
     int num_sms = 148;
 };
 
@@ -84,7 +85,8 @@ bool encoder_forward(Encoder* enc, cudaStream_t stream, const uint16_t* tok_stor
 bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const float* b, __half* out, int rows,
                       int hidden, float eps);
 // qkv is head-major: [heads][n_tokens][3 * head_dim] (q | k | v per token)
-bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
-                      int max_pos, int n_seq, int n_tokens, int hidden, int heads, __half* ctx);
+bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int* items,
+                      int* item_count, int row_base, int max_pos, int n_seq, int n_tokens, int hidden, int heads,
+                      __half* ctx, bool build_items);
 
 }  // namespace lb2

@@ -179,18 +179,31 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Input is HEAD-MAJOR: qkv[head][token][q(hd) | k(hd) | v(hd)], written that way by the QKV GEMM's
 // grouped TMA store, so one (sequence, head) is a single contiguous run of L * 3hd halves: every DRAM
 // line fetched is fully used (the token-major layout cost 2.7x the algorithmic DRAM reads, ncu).
-// blockIdx.x = query block, so the CTAs sharing a (sequence, head)'s keys are launched back to back.
+// blockIdx.x walks a work list of (passage, query block) items in which a passage's blocks are adjacent, so
+// the CTAs sharing a (sequence, head)'s keys are launched back to back; no CTA is launched for nothing.
+// work list of the attention kernel for one encoder pass: one item per (passage, 64-row query block)
+__global__ void attention_items_kernel(const int32_t* __restrict__ seq_len, int n_seq, int* __restrict__ items,
+                                       int* __restrict__ count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    const int nb = (seq_len[s] + 63) >> 6;
+    const int base = atomicAdd(count, nb);
+    for (int i = 0; i < nb; i++) items[base + i] = s * 8 + i;  // a passage's blocks stay adjacent: they share K/V in L2
+}
+
 template <int HD>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, HD == 32 ? 8 : 4)
 attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ seq_start,
-                 const int32_t* __restrict__ seq_len, int row_base, int n_tokens, int hidden, __half* __restrict__ ctx) {
+                 const int32_t* __restrict__ seq_len, const int* __restrict__ items, const int* __restrict__ n_items,
+                 int row_base, int n_tokens, int hidden, __half* __restrict__ ctx) {
     constexpr int P = HD + 8;  // row pitch in halves: 16-byte aligned rows, conflict-free ldmatrix
     __shared__ __align__(16) __half Ks[2][64 * P];
     __shared__ __align__(16) __half Vs[2][64 * P];
-    const int s = blockIdx.z, h = blockIdx.y;
+    if (static_cast<int>(blockIdx.x) >= *n_items) return;  // the grid is sized from a host-side upper bound
+    const int item = items[blockIdx.x];
+    const int s = item >> 3, h = blockIdx.y;
     const int L = seq_len[s];
-    const int qblk0 = blockIdx.x * 64;
-    if (qblk0 >= L) return;
+    const int qblk0 = (item & 7) * 64;
     const int row0 = seq_start[s] - row_base;
     constexpr int ld = 3 * HD;
     const __half* qbase = qkv + (static_cast<size_t>(h) * n_tokens + row0) * ld;
@@ -391,16 +404,23 @@ bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const fl
     return true;
 }
 
-bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int row_base,
-                      int max_pos, int n_seq, int n_tokens, int hidden, int heads, __half* ctx) {
+bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int* items,
+                      int* item_count, int row_base, int max_pos, int n_seq, int n_tokens, int hidden, int heads,
+                      __half* ctx, bool build_items) {
     if (n_seq <= 0) return true;
     const int hd = hidden / heads;
-    if (n_seq > 65535) { set_error("attention: more than 65535 passages in one pass"); return false; }
-    dim3 grid((max_pos + 63) / 64, heads, n_seq);
+    if (max_pos > 512) { set_error("attention: max_pos %d > 512", max_pos); return false; }
+    if (build_items) {  // once per encoder pass: the list is the same for every layer
+        LB2_CUDA_OK(cudaMemsetAsync(item_count, 0, sizeof(int), s));
+        attention_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_len, n_seq, items, item_count);
+        LB2_CUDA_OK(cudaGetLastError());
+    }
+    // sum_s ceil(L_s / 64) <= n_tokens / 64 + n_seq
+    dim3 grid(n_tokens / 64 + n_seq, heads);
     if (hd == 32)
-        attention_kernel<32><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, n_tokens, hidden, ctx);
+        attention_kernel<32><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, items, item_count, row_base, n_tokens, hidden, ctx);
     else if (hd == 64)
-        attention_kernel<64><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, row_base, n_tokens, hidden, ctx);
+        attention_kernel<64><<<grid, 128, 0, s>>>(qkv, seq_start, seq_len, items, item_count, row_base, n_tokens, hidden, ctx);
     else {
         set_error("attention: unsupported head_dim %d", hd);
         return false;
@@ -546,6 +566,8 @@ void encoder_free(Encoder* enc) {
     }
     if (enc->seq_len) cudaFree(enc->seq_len);
     enc->seq_len = nullptr;
+    if (enc->att_items) cudaFree(enc->att_items);
+    enc->att_items = nullptr;
     enc->cap_tokens = enc->cap_seqs = 0;
     enc->loaded = false;
 }
@@ -556,6 +578,9 @@ bool encoder_reserve(Encoder* enc, int64_t tokens, int64_t seqs) {
         enc->seq_len = nullptr;
         enc->cap_seqs = 0;
         LB2_CUDA_OK(cudaMalloc(&enc->seq_len, static_cast<size_t>(seqs) * sizeof(int32_t)));
+        if (enc->att_items) cudaFree(enc->att_items);
+        enc->att_items = nullptr;
+        LB2_CUDA_OK(cudaMalloc(&enc->att_items, (static_cast<size_t>(seqs) * 8 + 1) * sizeof(int)));  // [seqs * 8] items + count
         enc->cap_seqs = seqs;
     }
     if (tokens <= enc->cap_tokens) return true;
@@ -598,7 +623,9 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
         const LayerWeights& w = enc->layers[l];
         if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS, 3 * (H / c.heads))) return false;
         prof_begin(st, PROF_ATTN);
-        if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, row_base, c.max_pos, n_seq, T, H, c.heads, enc->ctx)) return false;
+        if (!launch_attention(st, enc->qkv, seq_start, enc->seq_len, enc->att_items, enc->att_items + enc->cap_seqs * 8,
+                              row_base, c.max_pos, n_seq, T, H, c.heads, enc->ctx, l == 0))
+            return false;
         prof_end(st, PROF_ATTN, 0);
         if (!gemm(enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, enc->y, H, H, EPI_BIAS_RES)) return false;
         prof_begin(st, PROF_NORM);
