@@ -350,7 +350,12 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { set_error("traversal step failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
             const HopCtrl c = *x->h_ctrl;
-            if (c.n_unique == 0) break;  // every slot idle: all queries done
+            if (c.n_done >= nq) break;  // every query has written its results
+            if (c.n_unique == 0) {
+                // call scope: every node requested in this hop already has its embedding; hop scope: cannot happen
+                if (!s.call_scope) { set_error("internal: traversal stalled (%d of %lld queries done)", c.n_done, (long long)nq); return LB2_ERR_CUDA; }
+                continue;
+            }
             if (c.n_unique > x->cap_unique || s.row_base_hop + (int64_t)c.n_unique > x->cap_E_rows) {
                 set_error("internal: hop work list overflow");
                 return LB2_ERR_CUDA;
