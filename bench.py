@@ -132,8 +132,9 @@ def build_world(args, rank, device):
     # 3. exact ground truth (brute-force fp32 IP over the same embeddings: run_evaluation.py:358-367 with k=10)
     Qt = torch.from_numpy(Q).to(E.device)
     gt = torch.empty((Qt.shape[0], 10), dtype=torch.int64, device=E.device)
-    for b0 in range(0, Qt.shape[0], 2048):
-        gt[b0:b0 + 2048] = torch.topk(Qt[b0:b0 + 2048] @ E.T, 10, dim=1).indices
+    gb = max(64, min(2048, (1 << 32) // max(1, corpus.n)))  # keep the score block around 16 GB
+    for b0 in range(0, Qt.shape[0], gb):
+        gt[b0:b0 + gb] = torch.topk(Qt[b0:b0 + gb] @ E.T, 10, dim=1).indices
     gt = gt.cpu().numpy()
     del E, Qt
     torch.cuda.empty_cache()
