@@ -106,6 +106,7 @@ int lb2_info(const lb2_index* idx, lb2_index_info* out);
 
 /* Stored-vector mode (non-pruned index): x is [ntotal, d] fp32. */
 int lb2_set_vectors(lb2_index* idx, const float* x);
+int lb2_set_vectors_device(lb2_index* idx, const float* d_x); /* same, source already in device memory */
 
 /* Pre-tokenised passage store: passage i = tokens[offsets[i] .. offsets[i+1]) (WordPiece ids incl.
  * [CLS]/[SEP], as the reference's tokenizer would produce them), ntotal+1 offsets. */

@@ -15,7 +15,8 @@ _LIB_PATH = Path(__file__).resolve().parent / "libleann_b200.so"
 _lib = None
 
 EXPORTED_SYMBOLS = [
-    "lb2_last_error", "lb2_version", "lb2_open", "lb2_close", "lb2_info", "lb2_set_vectors", "lb2_set_passages",
+    "lb2_last_error", "lb2_version", "lb2_open", "lb2_close", "lb2_info", "lb2_set_vectors", "lb2_set_vectors_device",
+    "lb2_set_passages",
     "lb2_encoder_weight_count", "lb2_set_encoder", "lb2_default_params", "lb2_search", "lb2_search_device",
     "lb2_last_query_stats", "lb2_encode_ids", "lb2_encode_tokens", "lb2_encode_range_device", "lb2_configure",
     "lb2_set_option",
@@ -72,6 +73,7 @@ def load():
     lib.lb2_close.restype = None
     lib.lb2_info.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
     lib.lb2_set_vectors.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lb2_set_vectors_device.argtypes = [C.c_void_p, C.c_void_p]
     lib.lb2_set_passages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lb2_encoder_weight_count.restype = C.c_size_t
     lib.lb2_encoder_weight_count.argtypes = [C.POINTER(EncoderConfig)]
@@ -152,6 +154,10 @@ class Index:
         if x.shape != (self.info.ntotal, self.info.d):
             raise ValueError(f"vectors must be [{self.info.ntotal}, {self.info.d}], got {x.shape}")
         _check(self._lib.lb2_set_vectors(self._h, _np_ptr(x)), "lb2_set_vectors")
+
+    def set_vectors_device(self, d_ptr: int):
+        _check(self._lib.lb2_set_vectors_device(self._h, C.c_void_p(d_ptr)), "lb2_set_vectors_device")
+        self.refresh_info()
 
     def set_passages(self, tokens: np.ndarray, offsets: np.ndarray):
         tokens = np.ascontiguousarray(tokens, np.uint16)

@@ -545,6 +545,15 @@ int lb2_set_vectors(lb2_index* x, const float* v) {
     return LB2_OK;
 }
 
+int lb2_set_vectors_device(lb2_index* x, const float* d_v) {
+    if (!x || !d_v) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (!use_device(x)) return LB2_ERR_CUDA;
+    const size_t n = (size_t)x->g.ntotal * x->g.d;
+    if (!dev_alloc(&x->d_vectors, n)) return LB2_ERR_CUDA;
+    if (cudaMemcpy(x->d_vectors, d_v, n * 4, cudaMemcpyDeviceToDevice) != cudaSuccess) { set_error("vector copy failed"); return LB2_ERR_CUDA; }
+    return LB2_OK;
+}
+
 int lb2_set_passages(lb2_index* x, const uint16_t* tokens, const uint64_t* offsets) {
     if (!x || !tokens || !offsets) { set_error("null argument"); return LB2_ERR_ARG; }
     if (!use_device(x)) return LB2_ERR_CUDA;
