@@ -345,7 +345,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out), flush=True)
+        emit(REAL_STDOUT, out)
 
 
 def _encoder_flops(W, agg):
@@ -401,7 +401,7 @@ def run_reference(args):
         return
     import torch
     if not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable": "set-up (corpus embedding + graph) needs the GPU encoder; no GPU here"}))
+        emit(REAL_STDOUT, {"impl": "reference", "unavailable": "set-up (corpus embedding + graph) needs the GPU encoder; no GPU here"})
         return
     from leann_b200 import build
     if build.needs_build():
@@ -425,11 +425,25 @@ def run_reference(args):
            "recall_at_10": res["recall_at_10"],
            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(REAL_STDOUT, out)
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, nvcc chatter of an on-demand build) write to fd 1; the contract is ONE JSON
+    line on stdout.  Point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def emit(real_fd, obj):
+    os.write(real_fd, (json.dumps(obj) + "\n").encode())
 
 
 if __name__ == "__main__":
     a = parse()
+    REAL_STDOUT = _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
