@@ -168,8 +168,12 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
     src, dst = src[m], dst[m]
     a = torch.cat([src, dst])
     b = torch.cat([dst, src])
-    key = torch.unique(a * n + b)
+    del src, dst, m
+    key = a * n + b
+    del a, b
+    key = torch.unique(key)
     a, b = key // n, key % n
+    del key
     xs = x.half() if x.is_cuda else x
     d = torch.empty(a.numel(), dtype=torch.float32, device=dev)
     step = 1 << 22  # edge chunks: the gathered [chunk, dim] operands stay small
@@ -179,8 +183,10 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
     # sort by (a, d): stable two-pass
     o = torch.argsort(d, stable=True)
     a, b, d = a[o], b[o], d[o]
+    del o
     o = torch.argsort(a, stable=True)
     a, b, d = a[o], b[o], d[o]
+    del o
     counts = torch.bincount(a, minlength=n)
     starts = torch.cumsum(counts, 0) - counts
     rank = torch.arange(a.numel(), device=dev) - starts[a]
