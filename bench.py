@@ -192,7 +192,7 @@ def run_b200(args):
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = dict(gpu_ms=0.0, encoder_ms=0.0, gemm_ms=0.0, gemm_flops=0.0, attention_ms=0.0, norm_ms=0.0, launches=0, ndis=0, nhops=0, n_recomputed=0,
-               n_requested=0, n_tokens=0, steps=0)
+               n_requested=0, n_tokens=0, steps=0, passes=0)
     recalls = []
     t_dev = 0.0
     for s in range(args.warmup, args.warmup + args.steps):
@@ -210,6 +210,7 @@ def run_b200(args):
             agg[key] += getattr(st, key)
         agg["launches"] += st.n_kernel_launches
         agg["steps"] += st.n_steps
+        agg["passes"] += (st.n_kernel_launches - 1 - 2 * st.n_steps) // (3 + 7 * W["preset"].layers)  # 45 launches per encoder pass
         recalls.append(recall_at_k(dI.cpu().numpy(), gt))
     barrier()
     clk = clocks.stop()
@@ -309,6 +310,19 @@ def run_b200(args):
         peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained, cuBLAS bf16 sustained)" if peaks else "fallback 1590"
         gemm_tf = agg["gemm_flops"] / (agg["gemm_ms"] / 1e3) / 1e12 if agg["gemm_ms"] > 0 else None
+        # DRAM traffic of the GEMM per launch: algorithmic bytes of the timed region's launches x the
+        # dram/algorithmic ratio of the committed ncu --set full capture (profiles/r01_final_gemm_traffic.json)
+        traffic = None
+        try:
+            tr = json.loads((ROOT / "profiles" / "r01_final_gemm_traffic.json").read_text())
+            p_ = W["preset"]
+            h, f = p_.hidden, p_.ffn
+            bytes_tok_layer = 2 * ((h + 3 * h) + (3 * h) + (h + f) + (f + 2 * h))  # A + C (+ residual) of the 4 GEMMs
+            n_gemm = agg["passes"] * 4 * p_.layers
+            if n_gemm > 0:
+                traffic = agg["n_tokens"] * p_.layers * bytes_tok_layer * tr["dram_over_algorithmic"] / n_gemm
+        except Exception:
+            pass
         lens = np.minimum(np.diff(W["corpus"].offsets.astype(np.int64)), W["preset"].max_pos)
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -324,7 +338,8 @@ def run_b200(args):
             "gpu_launches": int(agg["launches"]),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05)", "achieved": gemm_tf, "peak": peak,
-                         "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic,
+                         "traffic_note": "bytes per launch (average launch of the timed region); dram bytes = 1.01 x algorithmic in the ncu capture",
                          "peak_source": peak_src,
                          "share_of_step": agg["gemm_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None},
             "detail": {"ndis_per_query": agg["ndis"] / (nq * args.steps), "nhops_per_query": agg["nhops"] / (nq * args.steps),
