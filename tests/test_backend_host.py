@@ -65,3 +65,30 @@ def test_builder_writes_reference_format(tmp_path):
     g = read_compact_index(str(tmp_path / "t.index"))
     assert g.ntotal == 500 and g.vectors is not None
     assert np.allclose(np.linalg.norm(g.vectors, axis=1), 1, atol=1e-5)
+
+
+def test_registers_into_the_real_leann_registry_when_leann_is_importable():
+    """With the reference's own leann-core on the path, the backend lands in LEANN's BACKEND_REGISTRY and
+    implements LEANN's interfaces (what LeannSearcher looks up by meta['backend_name'], CORE/api.py:625-637)."""
+    import os
+    import subprocess
+    import sys
+    core = "/root/reference/packages/leann-core/src"
+    if not os.path.isdir(core):
+        pytest.skip("reference checkout not present (GPU box)")
+    code = (
+        "import leann.registry as r, leann.interface as i\n"
+        "import leann_b200.backend as b, leann_b200.interface as li\n"
+        "assert li.HAVE_LEANN\n"
+        "assert r.BACKEND_REGISTRY['hnsw_b200'] is b.B200HnswBackend\n"
+        "assert issubclass(b.B200HnswBackend, i.LeannBackendFactoryInterface)\n"
+        "assert issubclass(b.B200HnswSearcher, i.LeannBackendSearcherInterface)\n"
+        "assert issubclass(b.B200HnswBuilder, i.LeannBackendBuilderInterface)\n"
+        "import inspect\n"
+        "ref = inspect.signature(i.LeannBackendSearcherInterface.search).parameters\n"
+        "mine = inspect.signature(b.B200HnswSearcher.search).parameters\n"
+        "assert all(k in mine for k in ref if k != 'kwargs'), (list(ref), list(mine))\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=core + os.pathsep + str(__import__('pathlib').Path(__file__).resolve().parents[1]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -157,6 +157,36 @@ def test_recompute_search_is_exact_given_the_gpu_embeddings(lib, cuda_ok, rc, ca
     assert st.n_recomputed < st.n_requested  # cross-query de-duplication happened (shared entry point at least)
 
 
+def test_recompute_search_bge_base_768d_cls_pooling(lib, cuda_ok, tmp_path):
+    """Config-4 encoder family (bge-base: 12 layers, 768d, head_dim 64, CLS pooling) through the whole pipeline:
+    GPU search == oracle traversal over the GPU's own embeddings, and the embeddings match the fp32 BertModel."""
+    from leann_b200.graph_build import build_hnsw_graph
+    from oracle.binding import Oracle
+    from oracle.encoder_oracle import EncoderOracle
+    preset = synth.BGE_BASE
+    w = synth.synthetic_weights(preset, 3)
+    blob = synth.pack_weights(preset, w)
+    tm, corpus = synth.make_corpus(700, preset.vocab_size, seed=5, max_len=200)
+    queries = synth.make_queries(tm, 24, seed=6)
+    enc = open_encoder_only(preset, blob, corpus)
+    E = enc.encode_ids(np.arange(corpus.n))
+    Q = enc.encode_tokens(queries.tokens, queries.offsets)
+    ref = EncoderOracle(preset, w).encode_store(corpus.tokens, corpus.offsets, ids=range(16))
+    assert np.abs(E[:16] - ref).max() < 2e-3
+    g = build_hnsw_graph(E, M=8, metric="mips")
+    f = tmp_path / "bge.index"
+    csr.write_compact_index(str(f), g)
+    idx = capi.Index(str(f))
+    idx.set_passages(corpus.tokens, corpus.offsets)
+    idx.set_encoder(preset.config(), blob)
+    idx.configure(slots=12, passages_per_pass=128)
+    D, I = idx.search(Q, 10, capi.make_params(40, 2, recompute=True))
+    oD, oI, ond, onh = Oracle(g, E).search(Q, 10, ef=40, beam=2, nthreads=8)
+    assert np.array_equal(I, oI) and np.array_equal(D, oD)
+    nd, nh = idx.last_query_stats(len(Q))
+    assert np.array_equal(nd, ond) and np.array_equal(nh, onh)
+
+
 def test_call_scope_dedup_gives_identical_results_with_fewer_recomputes(lib, cuda_ok, rc):
     idx = capi.Index(str(rc["dir"] / "rc.index"))
     idx.set_passages(rc["corpus"].tokens, rc["corpus"].offsets)
