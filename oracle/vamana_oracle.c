@@ -65,8 +65,12 @@ void vo_pq_populate_chunk_distances(const vo_index* x, const float* tables_tr, c
         for (uint32_t j = x->chunk_offsets[chunk]; j < x->chunk_offsets[chunk + 1]; j++) {
             const float* centers_dim_vec = tables_tr + 256 * (size_t)j;
             for (int idx = 0; idx < 256; idx++) {
-                double diff = centers_dim_vec[idx] - query_vec[j]; /* float subtraction, then widened */
-                chunk_dists[idx] += (float)(diff * diff);
+                /* source: double diff = c - q (a float subtraction); chunk += (float)(diff * diff).  The product of two
+                 * floats is exact in double, so the cast rounds once — it IS the float product — and the reference's own
+                 * build flags (-O3 -mavx2 -mfma, GCC's default -ffp-contract=fast; DiskANN/CMakeLists.txt:429-441) fuse it
+                 * with the accumulation.  Verified against the compiled pq.cpp (tests/test_vamana_oracle.py). */
+                float diff = centers_dim_vec[idx] - query_vec[j];
+                chunk_dists[idx] = fmaf(diff, diff, chunk_dists[idx]);
             }
         }
     }
@@ -186,7 +190,8 @@ int vo_search(const vo_index* x, const float* tables_tr, const float* query, int
     /* :1822-1848 */
     if (x->metric == VO_MIPS || x->metric == VO_COSINE) {
         const int inherent = x->metric == VO_COSINE ? D : D - 1;
-        for (int i = 0; i < inherent; i++) { aq[i] = query[i]; query_norm += query[i] * query[i]; }
+        /* query_norm += q*q, contracted to an fma by the reference's build flags (see populate_chunk_distances) */
+        for (int i = 0; i < inherent; i++) { aq[i] = query[i]; query_norm = fmaf(query[i], query[i], query_norm); }
         if (x->metric == VO_MIPS) aq[D - 1] = 0;
         query_norm = sqrtf(query_norm);
         for (int i = 0; i < inherent; i++) aq[i] = aq[i] / query_norm;
