@@ -149,6 +149,74 @@ int lb2_configure(lb2_index* idx, int32_t slots, int32_t passages_per_pass);
  * passage lives in HBM until the call returns — identical results, fewer recomputes, nothing persists). */
 int lb2_set_option(lb2_index* idx, const char* key, int64_t value);
 
+/* ------------------------------------------------------------------------------------------------
+ * DiskANN / Vamana backend (leann-backend-diskann).  Same handle type; lb2_set_passages / lb2_set_encoder /
+ * lb2_encode_* / lb2_set_option / lb2_close work on it unchanged.
+ *
+ *   lb2_diskann_open     StaticDiskIndex<float>(metric, index_path_prefix, num_threads, num_nodes_to_cache,
+ *                          cache_mechanism, zmq_port, pq_prefix, partition_prefix)
+ *                          leann-backend-diskann/leann_backend_diskann/diskann_backend.py:363-372
+ *                          -> third_party/DiskANN/python/src/static_disk_index.cpp:15-48
+ *                          -> PQFlashIndex::load, third_party/DiskANN/src/pq_flash_index.cpp:887-911, 1017-1467
+ *                        Opens the same files: <p>_pq_pivots.bin, <p>_pq_compressed.bin, <p>_disk.index (+_medoids.bin,
+ *                        _centroids.bin, _max_base_norm.bin) or, with a partition prefix, <pp>_partition.bin and
+ *                        <pp>_disk_graph.index.
+ *   lb2_diskann_search   StaticDiskIndex::batch_search(queries, num_queries, knn, complexity, beam_width, num_threads,
+ *                          USE_DEFERRED_FETCH, skip_search_reorder, recompute_beighbor_embeddings, dedup_node_dis,
+ *                          prune_ratio, batch_recompute, global_pruning)
+ *                          diskann_backend.py:452-467 -> static_disk_index.cpp:88-118
+ *                          -> PQFlashIndex::cached_beam_search, pq_flash_index.cpp:1779-2906,
+ *                        including the deferred fetch_embeddings round trip (:2661-2759 -> diskann_embedding_server.py)
+ *                        which becomes one encoder pass over the de-duplicated expanded nodes of the whole batch.
+ *   lb2_diskann_params   the trailing arguments of batch_search; `metric` is given at open time as in the reference.
+ */
+typedef struct {
+    int32_t complexity;          /* L: candidate list size                                   (l_search)        */
+    int32_t beam_width;          /* nodes expanded per iteration                                               */
+    int32_t deferred_fetch;      /* USE_DEFERRED_FETCH = recompute_embeddings: re-rank from fresh embeddings   */
+    int32_t skip_search_reorder; /* keep PQ distances of the expanded nodes                                    */
+    int32_t recompute_neighbors; /* must be 0: LEANN always passes false (diskann_backend.py:449)              */
+    int32_t dedup_node_dis;      /* only meaningful with recompute_neighbors; accepted and ignored             */
+    int32_t batch_recompute;     /* with recompute_neighbors == 0 this only regroups identical work; ignored   */
+    int32_t global_pruning;      /* PQ pruning acts only inside recompute_neighbors (prune_node_nbrs,          */
+    float prune_ratio;           /*   pq_flash_index.cpp:2018-2021 returns at once otherwise); ignored         */
+    uint32_t io_limit;           /* 0 = unlimited (the python binding passes UINT32_MAX)                       */
+} lb2_diskann_params;
+
+typedef struct {
+    int64_t npts;
+    int32_t dim;            /* embedding dimension queries must have (data_dim - 1 for mips)   */
+    int32_t data_dim;       /* stored coordinate count = PQ dims                               */
+    int32_t n_chunks;       /* PQ bytes per vector                                             */
+    int32_t max_degree;
+    int32_t metric;         /* 0 l2, 1 mips, 2 cosine                                          */
+    int32_t n_medoids;
+    int32_t partitioned;    /* opened from <pp>_partition.bin + <pp>_disk_graph.index          */
+    int32_t has_coords;     /* full-precision coordinates loaded (recompute_embeddings=False)  */
+    float max_base_norm;
+    int32_t pad;
+    int64_t n_edges;
+} lb2_diskann_info_t;
+
+#define LB2_METRIC_L2 0
+#define LB2_METRIC_MIPS 1
+#define LB2_METRIC_COSINE 2
+
+lb2_index* lb2_diskann_open(const char* index_prefix, const char* partition_prefix /* NULL or "" = none */, int metric,
+                            int device);
+int lb2_diskann_info(const lb2_index* idx, lb2_diskann_info_t* out);
+void lb2_diskann_default_params(lb2_diskann_params* p);
+/* q: [nq, dim] host; D: [nq, k] host; I: [nq, k] host (ids widened to int64; -1 / FLT_MAX where fewer than k nodes
+ * were expanded).  Distances follow the reference: squared L2 for l2 and cosine (on unit vectors), and for mips
+ * -(L2 in the extended space) * max_base_norm * |q| (pq_flash_index.cpp:2873-2881). */
+int lb2_diskann_search(lb2_index* idx, int64_t nq, const float* q, int64_t k, float* D, int64_t* I,
+                       const lb2_diskann_params* params, lb2_search_stats* stats);
+int lb2_diskann_search_device(lb2_index* idx, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
+                              const lb2_diskann_params* params, lb2_search_stats* stats);
+/* test / diagnostics hook: the expanded nodes (full_retset) of the queries of the last search call, in expansion
+ * order; ids is [nq, cap], n_full [nq].  Valid for calls of at most one wave (4096 queries). */
+int lb2_diskann_last_expansions(lb2_index* idx, int64_t nq, int32_t cap, uint32_t* ids, int32_t* n_full);
+
 /* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
 int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);

@@ -79,9 +79,14 @@ class B200HnswBuilder(LeannBackendBuilderInterface):
         write_compact_index(str(path.parent / f"{path.stem}.index"), g)
 
 
-class B200HnswSearcher(LeannBackendSearcherInterface):
-    def __init__(self, index_path: str, **kwargs):
-        # --- BaseSearcher.__init__ contract (leann-core/src/leann/searcher_base.py:18-56)
+class _B200SearcherBase(LeannBackendSearcherInterface):
+    """What ``BaseSearcher`` gives the reference's searchers (leann-core/src/leann/searcher_base.py:18-160), with the
+    embedding *server* replaced by the in-process GPU recompute stage."""
+
+    _index: capi.Index
+
+    def _init_base(self, index_path: str, kwargs: dict) -> None:
+        # --- BaseSearcher.__init__ contract (searcher_base.py:18-56)
         self.index_path = Path(index_path)
         self.index_dir = self.index_path.parent
         self.meta = kwargs.get("meta") or self._load_meta()
@@ -92,27 +97,10 @@ class B200HnswSearcher(LeannBackendSearcherInterface):
             raise ValueError("Dimensions not found in Leann metadata.")
         self.embedding_model = self.meta.get("embedding_model")
         self.embedding_mode = self.meta.get("embedding_mode", "sentence-transformers")
-        # --- HNSWSearcher.__init__ (hnsw_backend.py:128-151)
-        self.distance_metric = self.meta.get("backend_kwargs", {}).get("distance_metric", "mips").lower()
-        _metric_enum(self.distance_metric)
-        self.is_compact = self.meta.get("is_compact", True)
-        self.is_pruned = self.meta.get("is_pruned", True)
-        index_file = self.index_dir / f"{self.index_path.stem}.index"
-        if not index_file.exists():
-            raise FileNotFoundError(f"HNSW index file not found at {index_file}")
-        if not self.is_compact:
-            raise RuntimeError("the B200 backend reads compact (CSR) HNSW indexes only")
         self.device = int(kwargs.get("device", os.environ.get("LOCAL_RANK", 0)))
-        self._index = capi.Index(str(index_file), self.device)
-        if self._index.info.d != int(self.dimensions):
-            raise ValueError(f"index dimension {self._index.info.d} != meta dimensions {self.dimensions}")
         self._tokenizer = None
         self._recompute_ready = False
         self.preset: synth.ModelPreset | None = None
-        if kwargs.get("slots") or kwargs.get("passages_per_pass"):
-            self._index.configure(int(kwargs.get("slots", 0)), int(kwargs.get("passages_per_pass", 0)))
-        if kwargs.get("dedup_scope") is not None:  # "hop" (default) | "call"
-            self._index.set_option("dedup_scope", {"hop": 0, "call": 1}[str(kwargs["dedup_scope"])])
 
     # ------------------------------------------------------------------ helpers
     def _load_meta(self) -> dict[str, Any]:
@@ -189,6 +177,35 @@ class B200HnswSearcher(LeannBackendSearcherInterface):
         emb = self._index.encode_tokens(toks, np.array([0, toks.size], np.uint64))
         return emb.reshape(1, -1)
 
+    @property
+    def last_stats(self) -> dict[str, Any]:
+        return self._index.last_stats.as_dict()
+
+    def cleanup(self):
+        self._index.close()
+
+
+class B200HnswSearcher(_B200SearcherBase):
+    def __init__(self, index_path: str, **kwargs):
+        self._init_base(index_path, kwargs)
+        # --- HNSWSearcher.__init__ (hnsw_backend.py:128-151)
+        self.distance_metric = self.meta.get("backend_kwargs", {}).get("distance_metric", "mips").lower()
+        _metric_enum(self.distance_metric)
+        self.is_compact = self.meta.get("is_compact", True)
+        self.is_pruned = self.meta.get("is_pruned", True)
+        index_file = self.index_dir / f"{self.index_path.stem}.index"
+        if not index_file.exists():
+            raise FileNotFoundError(f"HNSW index file not found at {index_file}")
+        if not self.is_compact:
+            raise RuntimeError("the B200 backend reads compact (CSR) HNSW indexes only")
+        self._index = capi.Index(str(index_file), self.device)
+        if self._index.info.d != int(self.dimensions):
+            raise ValueError(f"index dimension {self._index.info.d} != meta dimensions {self.dimensions}")
+        if kwargs.get("slots") or kwargs.get("passages_per_pass"):
+            self._index.configure(int(kwargs.get("slots", 0)), int(kwargs.get("passages_per_pass", 0)))
+        if kwargs.get("dedup_scope") is not None:  # "hop" (default) | "call"
+            self._index.set_option("dedup_scope", {"hop": 0, "call": 1}[str(kwargs["dedup_scope"])])
+
     def search(self, query: np.ndarray, top_k: int, zmq_port: Optional[int] = None, complexity: int = 64,
                beam_width: int = 1, prune_ratio: float = 0.0, recompute_embeddings: bool = True,
                pruning_strategy: Literal["global", "local", "proportional"] = "global", batch_size: int = 0,
@@ -226,13 +243,6 @@ class B200HnswSearcher(LeannBackendSearcherInterface):
             raise RuntimeError(str(e)) from e
         string_labels = [[str(int_label) for int_label in batch_labels] for batch_labels in labels]
         return {"labels": string_labels, "distances": distances}
-
-    @property
-    def last_stats(self) -> dict[str, Any]:
-        return self._index.last_stats.as_dict()
-
-    def cleanup(self):
-        self._index.close()
 
 
 @register_backend(BACKEND_NAME)

@@ -20,6 +20,8 @@ EXPORTED_SYMBOLS = [
     "lb2_encoder_weight_count", "lb2_set_encoder", "lb2_default_params", "lb2_search", "lb2_search_device",
     "lb2_last_query_stats", "lb2_encode_ids", "lb2_encode_tokens", "lb2_encode_range_device", "lb2_configure",
     "lb2_set_option",
+    "lb2_diskann_open", "lb2_diskann_info", "lb2_diskann_default_params", "lb2_diskann_search",
+    "lb2_diskann_search_device", "lb2_diskann_last_expansions",
     "lb2_test_gemm_f16", "lb2_test_gemm_grouped_f16", "lb2_test_layernorm_f16", "lb2_test_attention_f16",
 ]
 
@@ -51,6 +53,22 @@ class EncoderConfig(C.Structure):
     _fields_ = [("vocab_size", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
                 ("ffn", C.c_int32), ("max_pos", C.c_int32), ("type_vocab", C.c_int32), ("ln_eps", C.c_float),
                 ("pooling", C.c_int32), ("normalize", C.c_int32)]
+
+
+class DiskannParams(C.Structure):
+    _fields_ = [("complexity", C.c_int32), ("beam_width", C.c_int32), ("deferred_fetch", C.c_int32),
+                ("skip_search_reorder", C.c_int32), ("recompute_neighbors", C.c_int32), ("dedup_node_dis", C.c_int32),
+                ("batch_recompute", C.c_int32), ("global_pruning", C.c_int32), ("prune_ratio", C.c_float),
+                ("io_limit", C.c_uint32)]
+
+
+class DiskannInfo(C.Structure):
+    _fields_ = [("npts", C.c_int64), ("dim", C.c_int32), ("data_dim", C.c_int32), ("n_chunks", C.c_int32),
+                ("max_degree", C.c_int32), ("metric", C.c_int32), ("n_medoids", C.c_int32), ("partitioned", C.c_int32),
+                ("has_coords", C.c_int32), ("max_base_norm", C.c_float), ("pad", C.c_int32), ("n_edges", C.c_int64)]
+
+
+DISKANN_METRICS = {"l2": 0, "mips": 1, "cosine": 2}
 
 
 def library_path() -> Path:
@@ -90,6 +108,15 @@ def load():
     lib.lb2_encode_range_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.lb2_configure.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.lb2_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.lb2_diskann_open.restype = C.c_void_p
+    lib.lb2_diskann_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    lib.lb2_diskann_info.argtypes = [C.c_void_p, C.POINTER(DiskannInfo)]
+    lib.lb2_diskann_default_params.argtypes = [C.POINTER(DiskannParams)]
+    lib.lb2_diskann_default_params.restype = None
+    for name in ("lb2_diskann_search", "lb2_diskann_search_device"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.POINTER(DiskannParams), C.POINTER(SearchStats)]
+    lib.lb2_diskann_last_expansions.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.lb2_test_gemm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int]
     lib.lb2_test_layernorm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
@@ -220,3 +247,57 @@ class Index:
     def encode_range_device(self, first: int, n: int, d_out: int):
         _check(self._lib.lb2_encode_range_device(self._h, int(first), int(n), C.c_void_p(d_out)),
                "lb2_encode_range_device")
+
+
+def make_diskann_params(complexity=64, beam_width=1, recompute_embeddings=True, skip_search_reorder=False,
+                        recompute_neighbors=False, dedup_node_dis=False, prune_ratio=0.0, batch_recompute=False,
+                        global_pruning=True, io_limit=0) -> DiskannParams:
+    """Argument-for-argument the tail of StaticDiskIndex::batch_search (static_disk_index.cpp:88-93)."""
+    return DiskannParams(int(complexity), int(beam_width), int(bool(recompute_embeddings)), int(bool(skip_search_reorder)),
+                         int(bool(recompute_neighbors)), int(bool(dedup_node_dis)), int(bool(batch_recompute)),
+                         int(bool(global_pruning)), float(prune_ratio), int(io_limit))
+
+
+class DiskannIndex(Index):
+    """Owning wrapper of a handle opened with lb2_diskann_open; passages / encoder / encode_* as on Index."""
+
+    def __init__(self, index_prefix: str, metric: str = "mips", partition_prefix: str | None = None, device: int = 0):
+        lib = load()
+        if metric.lower() not in DISKANN_METRICS:
+            raise ValueError(f"Unsupported distance_metric '{metric}'.")
+        h = lib.lb2_diskann_open(str(index_prefix).encode(), (partition_prefix or "").encode(),
+                                 DISKANN_METRICS[metric.lower()], int(device))
+        if not h:
+            raise Lb2Error(f"lb2_diskann_open('{index_prefix}') failed: {lib.lb2_last_error().decode('utf-8', 'replace')}")
+        self._h = C.c_void_p(h)
+        self._lib = lib
+        self.info = IndexInfo()
+        _check(lib.lb2_info(self._h, C.byref(self.info)), "lb2_info")
+        self.dinfo = DiskannInfo()
+        _check(lib.lb2_diskann_info(self._h, C.byref(self.dinfo)), "lb2_diskann_info")
+        self.last_stats = SearchStats()
+
+    def search(self, q: np.ndarray, k: int, params: DiskannParams | None = None):
+        q = np.ascontiguousarray(q, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dinfo.dim:
+            raise ValueError(f"query must be [B, {self.dinfo.dim}], got {q.shape}")
+        nq = q.shape[0]
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        p = params or make_diskann_params()
+        _check(self._lib.lb2_diskann_search(self._h, nq, _np_ptr(q), int(k), _np_ptr(D), _np_ptr(I), C.byref(p),
+                                            C.byref(self.last_stats)), "lb2_diskann_search")
+        return D, I
+
+    def search_device(self, d_q: int, nq: int, k: int, d_D: int, d_I: int, params: DiskannParams | None = None):
+        p = params or make_diskann_params()
+        _check(self._lib.lb2_diskann_search_device(self._h, int(nq), C.c_void_p(d_q), int(k), C.c_void_p(d_D),
+                                                   C.c_void_p(d_I), C.byref(p), C.byref(self.last_stats)),
+               "lb2_diskann_search_device")
+
+    def last_expansions(self, nq: int, cap: int):
+        ids = np.empty((nq, cap), np.uint32)
+        n_full = np.empty(nq, np.int32)
+        _check(self._lib.lb2_diskann_last_expansions(self._h, nq, cap, _np_ptr(ids), _np_ptr(n_full)),
+               "lb2_diskann_last_expansions")
+        return ids, n_full

@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "index_io.h"
 #include "traverse.cuh"
+#include "vamana.cuh"
+#include "vamana_io.h"
 
 namespace lb2 {
 
@@ -155,6 +157,21 @@ struct lb2_index {
     int64_t cap_enc = 0;
     bool profile_gemm = false;
     EventPool ev_total, ev_enc;
+    // ---- DiskANN / Vamana handle (lb2_diskann_open)
+    bool is_vamana = false;
+    DevVamana vam;
+    bool vam_partitioned = false;
+    int64_t vam_edges = 0;
+    int32_t* dv_nbrs = nullptr; uint8_t* dv_codes = nullptr; float* dv_tables_tr = nullptr; float* dv_centroid = nullptr;
+    uint32_t* dv_chunk_offsets = nullptr; uint32_t* dv_medoids = nullptr; float* dv_centroid_data = nullptr; float* dv_coords = nullptr;
+    VamanaWork vw{};           // buffers of the current wave (grow-only)
+    int64_t vcap_q = 0;        // queries aq/qrot/qnorm/lut/full_*/n_full are sized for
+    int vcap_full = 0, vcap_slots = 0;
+    int64_t vcap_uniq = 0;     // uniq_node / seq_start entries
+    int64_t vcap_E = 0;        // rows of d_vE
+    float* d_vE = nullptr;
+    bool vis_dirty = false;
+    int64_t v_last_wave = 0;
 };
 
 namespace lb2 {
@@ -259,6 +276,7 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
                 const lb2_search_params* prm, lb2_search_stats* stats) {
     lb2_search_params P;
     if (prm) P = *prm; else lb2_default_params(&P);
+    if (x->is_vamana) { set_error("this handle is a DiskANN index: use lb2_diskann_search"); return LB2_ERR_STATE; }
     if (nq < 0 || k <= 0 || k > 4096) { set_error("bad nq/k (nq=%lld k=%lld)", (long long)nq, (long long)k); return LB2_ERR_ARG; }
     if (P.efSearch <= 0 || P.efSearch > 16384) { set_error("efSearch out of range: %d", P.efSearch); return LB2_ERR_ARG; }
     if (P.pq_pruning_ratio != 0.f || P.local_prune || P.send_neigh_times_ratio != 0.f) {
@@ -451,6 +469,212 @@ int encode_impl(lb2_index* x, const uint16_t* d_tok, const uint64_t* d_off, cons
     return LB2_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ DiskANN / Vamana
+void free_vamana(lb2_index* x) {
+    dev_free(&x->dv_nbrs); dev_free(&x->dv_codes); dev_free(&x->dv_tables_tr); dev_free(&x->dv_centroid);
+    dev_free(&x->dv_chunk_offsets); dev_free(&x->dv_medoids); dev_free(&x->dv_centroid_data); dev_free(&x->dv_coords);
+    VamanaWork& w = x->vw;
+    dev_free(&w.aq); dev_free(&w.qnorm); dev_free(&w.qrot); dev_free(&w.lut); dev_free(&w.visited); dev_free(&w.full_ids);
+    dev_free(&w.full_dist); dev_free(&w.n_full); dev_free(&w.next_query); dev_free(&w.error_flag); dev_free(&w.stamp);
+    dev_free(&w.slot_of); dev_free(&w.claim); dev_free(&w.uniq_node); dev_free(&w.seq_start);
+    dev_free(&x->d_vE);
+    x->vcap_q = 0; x->vcap_full = 0; x->vcap_slots = 0; x->vcap_uniq = 0; x->vcap_E = 0;
+}
+
+template <class T>
+bool upload(T** dst, const std::vector<T>& src) {
+    if (src.empty()) return true;
+    if (!dev_alloc(dst, src.size())) return false;
+    if (cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("uploading the index failed");
+        return false;
+    }
+    return true;
+}
+
+constexpr int64_t VAM_WAVE = 4096;  // queries per wave: bounds the per-query tables (LUT = n_chunks KB per query)
+
+bool ensure_vamana_work(lb2_index* x, int64_t wave, int L, int beam, int cap_full, bool deferred) {
+    VamanaWork& w = x->vw;
+    const DevVamana& v = x->vam;
+    if (x->vcap_q < wave || x->vcap_full < cap_full) {
+        const size_t q = (size_t)std::max(wave, x->vcap_q), cf = (size_t)std::max(cap_full, x->vcap_full);
+        if (!dev_alloc(&w.aq, q * v.data_dim) || !dev_alloc(&w.qrot, q * v.data_dim) || !dev_alloc(&w.qnorm, q) ||
+            !dev_alloc(&w.lut, q * v.n_chunks * 256) || !dev_alloc(&w.full_ids, q * cf) || !dev_alloc(&w.full_dist, q * cf) ||
+            !dev_alloc(&w.n_full, q))
+            return false;
+        x->vcap_q = (int64_t)q; x->vcap_full = (int)cf;
+    }
+    if (!w.next_query && (!dev_alloc(&w.next_query, 1) || !dev_alloc(&w.error_flag, 1) || !dev_alloc(&w.claim, 1))) return false;
+    w.L = L; w.beam = beam; w.cap_full = x->vcap_full;
+    const int slots = vamana_search_slots(w, x->num_sms);
+    w.vis_words = ((v.n + 31) / 32 + 3) & ~int64_t(3);
+    if (x->vcap_slots < slots) {
+        if (!dev_alloc(&w.visited, (size_t)slots * (size_t)w.vis_words)) return false;
+        x->vcap_slots = slots;
+        x->vis_dirty = true;
+    }
+    w.slots = slots;
+    if (x->vis_dirty) {
+        if (cudaMemsetAsync(w.visited, 0, (size_t)x->vcap_slots * (size_t)w.vis_words * 4, x->stream) != cudaSuccess) { set_error("memset(visited) failed"); return false; }
+        x->vis_dirty = false;
+    }
+    if (deferred) {
+        if (!w.stamp) {
+            if (!dev_alloc(&w.stamp, (size_t)v.n) || !dev_alloc(&w.slot_of, (size_t)v.n)) return false;
+            if (cudaMemsetAsync(w.stamp, 0, (size_t)v.n * 4, x->stream) != cudaSuccess) { set_error("memset(stamp) failed"); return false; }
+            x->epoch = 0;
+        }
+        const int64_t need = wave * (int64_t)x->vcap_full;
+        if (x->vcap_uniq < need) {
+            if (!dev_alloc(&w.uniq_node, (size_t)need) || !dev_alloc(&w.seq_start, (size_t)need)) return false;
+            x->vcap_uniq = need;
+        }
+        const int need_chunks = (int)(need / x->per_pass) + 2;
+        if (!x->h_ctrl || x->max_chunks < need_chunks) {
+            if (x->h_ctrl) cudaFreeHost(x->h_ctrl);
+            if (x->h_bounds) cudaFreeHost(x->h_bounds);
+            x->h_ctrl = nullptr; x->h_bounds = nullptr;
+            x->max_chunks = need_chunks;
+            if (cudaHostAlloc(reinterpret_cast<void**>(&x->h_ctrl), sizeof(HopCtrl), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostAlloc(reinterpret_cast<void**>(&x->h_bounds), sizeof(int) * (x->max_chunks + 2), cudaHostAllocMapped) != cudaSuccess) {
+                set_error("pinned control block allocation failed");
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+int diskann_search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
+                        const lb2_diskann_params* prm, lb2_search_stats* stats) {
+    if (!x->is_vamana) { set_error("this handle is an HNSW index: use lb2_search"); return LB2_ERR_STATE; }
+    lb2_diskann_params P;
+    if (prm) P = *prm; else lb2_diskann_default_params(&P);
+    if (nq < 0 || k <= 0 || k > 4096) { set_error("bad nq/k (nq=%lld k=%lld)", (long long)nq, (long long)k); return LB2_ERR_ARG; }
+    if (P.complexity <= 0 || P.complexity > 16384) { set_error("complexity out of range: %d", P.complexity); return LB2_ERR_ARG; }
+    if (P.beam_width <= 0 || P.beam_width > 512) { set_error("beam_width out of range: %d", P.beam_width); return LB2_ERR_ARG; }
+    if (P.recompute_neighbors) {
+        set_error("recompute_neighbors=1 (per-hop neighbour recompute inside DiskANN) is not implemented; LEANN never sets it");
+        return LB2_ERR_UNSUPPORTED;
+    }
+    const DevVamana& v = x->vam;
+    const bool deferred = P.deferred_fetch != 0, skip = P.skip_search_reorder != 0;
+    if (deferred && (!x->d_tokens || !x->enc.loaded)) {
+        set_error("deferred fetch (recompute_embeddings) needs lb2_set_passages() and lb2_set_encoder() first");
+        return LB2_ERR_STATE;
+    }
+    if (deferred && x->enc.cfg.hidden != v.raw_dim) {
+        set_error("encoder hidden size %d != index dimension %d", x->enc.cfg.hidden, v.raw_dim);
+        return LB2_ERR_STATE;
+    }
+    if (!deferred && !skip && !v.coords) {
+        set_error("recompute_embeddings=False needs the full-precision coordinates of <prefix>_disk.index (not read in partition mode)");
+        return LB2_ERR_STATE;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (nq == 0) return LB2_OK;
+    cudaStream_t st = x->stream;
+    if (x->cap_qstats < nq) {
+        if (!dev_alloc(&x->d_qndis, (size_t)nq) || !dev_alloc(&x->d_qnhops, (size_t)nq)) return LB2_ERR_CUDA;
+        x->cap_qstats = nq;
+    }
+    x->last_nq = nq;
+    const int L = P.complexity, beam = P.beam_width;
+    const int cap_full = 4 * L + 2 * beam + 64;
+    const int64_t wave = std::min<int64_t>(nq, VAM_WAVE);
+    if (!ensure_vamana_work(x, wave, L, beam, cap_full, deferred)) return LB2_ERR_CUDA;
+    if (deferred && !encoder_reserve(&x->enc, (int64_t)x->per_pass * x->enc.cfg.max_pos, x->per_pass)) return LB2_ERR_CUDA;
+
+    x->ev_total.total_ms = 0; x->ev_enc.total_ms = 0;
+    for (auto& pl : g_prof_pool) pl.total_ms = 0;
+    g_gemm_flops = 0;
+    g_prof_on = x->profile_gemm;
+    cudaEventRecord(x->ev_total.get(), st);
+    long long launches = 0, n_recomputed = 0, n_tokens = 0, n_waves = 0, n_requested = 0;
+    VamanaWork& w = x->vw;
+    for (int64_t q0 = 0; q0 < nq; q0 += wave) {
+        const int64_t wq = std::min(wave, nq - q0);
+        w.nq = wq; w.k = (int)k; w.flags = (deferred ? VAM_DEFERRED_FETCH : 0) | (skip ? VAM_SKIP_SEARCH_REORDER : 0);
+        w.io_limit = P.io_limit ? P.io_limit : 0xffffffffu;
+        w.queries = d_q + q0 * v.raw_dim;
+        w.cmps = x->d_qndis + q0; w.hops = x->d_qnhops + q0;
+        w.outD = d_D + q0 * k; w.outI = d_I + q0 * k;
+        w.tok_off = x->d_tok_off; w.max_pos = x->enc.cfg.max_pos;
+        cudaMemsetAsync(w.error_flag, 0, sizeof(int), st);
+        if (!vamana_launch_prepare(st, v, w) || !vamana_launch_search(st, v, w, x->num_sms)) return LB2_ERR_CUDA;
+        launches += 3 + (wq + 65534) / 65535 - 1;
+        n_waves++;
+        if (deferred) {
+            x->epoch++;
+            w.call_epoch = x->epoch;
+            cudaMemsetAsync(w.claim, 0, sizeof(unsigned long long), st);
+            if (!vamana_launch_collect(st, v, w)) return LB2_ERR_CUDA;
+            gather_bounds_kernel<<<1, 64, 0, st>>>(w.claim, w.error_flag, w.seq_start, x->per_pass, x->h_ctrl, x->h_bounds, x->max_chunks);
+            launches += 2;
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { set_error("vamana traversal failed: %s", cudaGetErrorString(e)); x->vis_dirty = true; return LB2_ERR_CUDA; }
+            const HopCtrl c = *x->h_ctrl;
+            if (c.n_done != 0) { set_error("a query expanded more than %d nodes (complexity %d)", cap_full, L); x->vis_dirty = true; return LB2_ERR_CUDA; }
+            if (c.n_unique > x->vcap_uniq) { set_error("internal: vamana work list overflow"); return LB2_ERR_CUDA; }
+            if (x->vcap_E < c.n_unique) {
+                if (!dev_alloc(&x->d_vE, (size_t)c.n_unique * v.raw_dim)) { x->vcap_E = 0; return LB2_ERR_CUDA; }
+                x->vcap_E = c.n_unique;
+            }
+            n_recomputed += c.n_unique;
+            n_tokens += c.n_tokens;
+            cudaEventRecord(x->ev_enc.get(), st);
+            for (int ch = 0; ch < c.n_chunks; ch++) {
+                const int first = ch * x->per_pass;
+                const int n_seq = std::min(x->per_pass, c.n_unique - first);
+                const int row_base = x->h_bounds[ch];
+                const int n_tok = x->h_bounds[ch + 1] - row_base;
+                if (!encoder_forward(&x->enc, st, x->d_tokens, x->d_tok_off, w.uniq_node + first, w.seq_start + first, row_base,
+                                     n_seq, n_tok, x->d_vE + (size_t)first * v.raw_dim))
+                    return LB2_ERR_CUDA;
+                launches += encoder_kernels_per_pass(x->enc);
+            }
+            cudaEventRecord(x->ev_enc.get(), st);
+            w.E = x->d_vE;
+        }
+        if (!vamana_launch_rerank(st, v, w)) return LB2_ERR_CUDA;
+        launches++;
+        x->v_last_wave = wq;
+    }
+    cudaEventRecord(x->ev_total.get(), st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    g_prof_on = false;
+    if (e != cudaSuccess) { set_error("diskann search failed: %s", cudaGetErrorString(e)); x->vis_dirty = true; return LB2_ERR_CUDA; }
+    int err_flag = 0;
+    cudaMemcpy(&err_flag, w.error_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    if (err_flag) { set_error("a query expanded more than %d nodes (complexity %d)", cap_full, L); x->vis_dirty = true; return LB2_ERR_CUDA; }
+    x->ev_total.drain(); x->ev_enc.drain();
+    for (auto& pl : g_prof_pool) pl.drain();
+    if (stats) {
+        std::vector<long long> a((size_t)nq), b((size_t)nq);
+        cudaMemcpy(a.data(), x->d_qndis, nq * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(b.data(), x->d_qnhops, nq * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int64_t i = 0; i < nq; i++) { stats->ndis += a[i]; stats->nhops += b[i]; }
+        if (nq <= VAM_WAVE) {
+            std::vector<int> nf((size_t)nq);
+            cudaMemcpy(nf.data(), w.n_full, nq * sizeof(int), cudaMemcpyDeviceToHost);
+            for (int64_t i = 0; i < nq; i++) n_requested += nf[i];
+        }
+        stats->n_requested = n_requested;
+        stats->n_recomputed = n_recomputed;
+        stats->n_tokens = n_tokens;
+        stats->n_steps = n_waves;
+        stats->n_kernel_launches = launches;
+        stats->gpu_ms = x->ev_total.total_ms;
+        stats->encoder_ms = x->ev_enc.total_ms;
+        stats->gemm_ms = g_prof_pool[PROF_GEMM].total_ms;
+        stats->gemm_flops = g_gemm_flops;
+        stats->attention_ms = g_prof_pool[PROF_ATTN].total_ms;
+        stats->norm_ms = g_prof_pool[PROF_NORM].total_ms;
+    }
+    return LB2_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -522,6 +746,7 @@ void lb2_close(lb2_index* x) {
     dev_free(&x->d_vectors); dev_free(&x->d_tokens); dev_free(&x->d_tok_off);
     dev_free(&x->d_q); dev_free(&x->d_D); dev_free(&x->d_I); dev_free(&x->d_qndis); dev_free(&x->d_qnhops);
     dev_free(&x->d_enc_node); dev_free(&x->d_enc_start); dev_free(&x->d_enc_out);
+    free_vamana(x);
     x->ev_total.destroy(); x->ev_enc.destroy();
     delete x;
 }
@@ -686,6 +911,110 @@ int lb2_encode_tokens(lb2_index* x, int64_t n, const uint16_t* tokens, const uin
     const int rc = encode_impl(x, dt, doff, offsets, n, nullptr, 0, out, false);
     dev_free(&dt); dev_free(&doff);
     return rc;
+}
+
+// ---------------------------------------------------------------- DiskANN / Vamana entry points
+void lb2_diskann_default_params(lb2_diskann_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->complexity = 64; p->beam_width = 1; p->deferred_fetch = 1; p->global_pruning = 1;
+}
+
+lb2_index* lb2_diskann_open(const char* index_prefix, const char* partition_prefix, int metric, int device) {
+    if (!index_prefix) { set_error("index_prefix is null"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available: libleann_b200 has no CPU path");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    VamanaHost h;
+    std::string err;
+    if (!read_diskann_index(index_prefix, partition_prefix, metric, &h, &err)) { set_error("%s", err.c_str()); return nullptr; }
+    lb2_index* x = new lb2_index();
+    x->device = device;
+    if (!use_device(x)) { delete x; return nullptr; }
+    x->num_sms = prop.multiProcessorCount;
+    x->profile_gemm = getenv("LB2_PROFILE_GEMM") && atoi(getenv("LB2_PROFILE_GEMM")) != 0;
+    x->is_vamana = true;
+    x->vam_partitioned = h.partitioned;
+    x->vam_edges = h.n_edges;
+    bool ok = upload(&x->dv_nbrs, h.nbrs) && upload(&x->dv_codes, h.codes) && upload(&x->dv_tables_tr, h.tables_tr) &&
+              upload(&x->dv_centroid, h.centroid) && upload(&x->dv_chunk_offsets, h.chunk_offsets) && upload(&x->dv_medoids, h.medoids) &&
+              upload(&x->dv_centroid_data, h.centroid_data) && upload(&x->dv_coords, h.coords);
+    if (!ok) { lb2_close(x); return nullptr; }
+    DevVamana& v = x->vam;
+    v.n = h.n; v.data_dim = h.data_dim; v.raw_dim = metric == LB2_METRIC_MIPS ? h.data_dim - 1 : h.data_dim;
+    v.metric = metric; v.R = h.R; v.n_chunks = h.n_chunks; v.n_medoids = (int)h.medoids.size();
+    v.nbrs = x->dv_nbrs; v.codes = x->dv_codes; v.tables_tr = x->dv_tables_tr; v.centroid = x->dv_centroid;
+    v.chunk_offsets = x->dv_chunk_offsets; v.medoids = x->dv_medoids; v.centroid_data = x->dv_centroid_data; v.coords = x->dv_coords;
+    v.max_base_norm = h.max_base_norm;
+    // the shared passage / encoder entry points size themselves from these
+    x->g.ntotal = h.n; x->g.d = v.raw_dim; x->g.metric_ip = metric != LB2_METRIC_L2; x->g.entry_point = (int)h.medoids[0];
+    x->n_edges = h.n_edges;
+    return x;
+}
+
+int lb2_diskann_info(const lb2_index* x, lb2_diskann_info_t* o) {
+    if (!x || !o) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (!x->is_vamana) { set_error("not a DiskANN handle"); return LB2_ERR_STATE; }
+    const DevVamana& v = x->vam;
+    o->npts = v.n; o->dim = v.raw_dim; o->data_dim = v.data_dim; o->n_chunks = v.n_chunks; o->max_degree = v.R; o->metric = v.metric;
+    o->n_medoids = v.n_medoids; o->partitioned = x->vam_partitioned; o->has_coords = v.coords != nullptr;
+    o->max_base_norm = v.max_base_norm; o->pad = 0; o->n_edges = x->vam_edges;
+    return LB2_OK;
+}
+
+int lb2_diskann_search_device(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
+                              const lb2_diskann_params* p, lb2_search_stats* s) {
+    if (!x || (nq > 0 && (!d_q || !d_D || !d_I))) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (!use_device(x)) return LB2_ERR_CUDA;
+    return diskann_search_impl(x, nq, d_q, k, d_D, d_I, p, s);
+}
+
+int lb2_diskann_search(lb2_index* x, int64_t nq, const float* q, int64_t k, float* D, int64_t* I, const lb2_diskann_params* p,
+                       lb2_search_stats* s) {
+    if (!x || (nq > 0 && (!q || !D || !I))) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (k <= 0) { set_error("k must be positive"); return LB2_ERR_ARG; }
+    if (!x->is_vamana) { set_error("this handle is an HNSW index: use lb2_search"); return LB2_ERR_STATE; }
+    if (!use_device(x)) return LB2_ERR_CUDA;
+    if (nq == 0) return LB2_OK;
+    if (x->cap_q < nq) { if (!dev_alloc(&x->d_q, (size_t)nq * x->g.d)) return LB2_ERR_CUDA; x->cap_q = nq; }
+    if (x->cap_out < nq * k) {
+        if (!dev_alloc(&x->d_D, (size_t)(nq * k)) || !dev_alloc(&x->d_I, (size_t)(nq * k))) return LB2_ERR_CUDA;
+        x->cap_out = nq * k;
+    }
+    if (cudaMemcpyAsync(x->d_q, q, (size_t)nq * x->g.d * 4, cudaMemcpyHostToDevice, x->stream) != cudaSuccess) {
+        set_error("query upload failed"); return LB2_ERR_CUDA;
+    }
+    const int rc = diskann_search_impl(x, nq, x->d_q, k, x->d_D, x->d_I, p, s);
+    if (rc != LB2_OK) return rc;
+    if (cudaMemcpyAsync(D, x->d_D, (size_t)(nq * k) * 4, cudaMemcpyDeviceToHost, x->stream) != cudaSuccess ||
+        cudaMemcpyAsync(I, x->d_I, (size_t)(nq * k) * 8, cudaMemcpyDeviceToHost, x->stream) != cudaSuccess ||
+        cudaStreamSynchronize(x->stream) != cudaSuccess) {
+        set_error("result download failed"); return LB2_ERR_CUDA;
+    }
+    return LB2_OK;
+}
+
+int lb2_diskann_last_expansions(lb2_index* x, int64_t nq, int32_t cap, uint32_t* ids, int32_t* n_full) {
+    if (!x || !ids || !n_full || cap <= 0) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (!x->is_vamana || nq != x->last_nq || nq > x->v_last_wave) { set_error("no expansion lists for %lld queries", (long long)nq); return LB2_ERR_ARG; }
+    if (!use_device(x)) return LB2_ERR_CUDA;
+    const VamanaWork& w = x->vw;
+    std::vector<int> nf((size_t)nq);
+    std::vector<uint32_t> all((size_t)nq * w.cap_full);
+    if (cudaMemcpy(nf.data(), w.n_full, nq * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(all.data(), w.full_ids, all.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("download failed"); return LB2_ERR_CUDA; }
+    for (int64_t q = 0; q < nq; q++) {
+        n_full[q] = nf[q];
+        for (int j = 0; j < cap; j++) ids[q * cap + j] = j < nf[q] && j < w.cap_full ? all[(size_t)q * w.cap_full + j] : 0xffffffffu;
+    }
+    return LB2_OK;
 }
 
 // ---------------------------------------------------------------- unit-test hooks

@@ -49,5 +49,24 @@ def write_leann_index(dirpath: Path, name: str, graph: csr.CSRGraph, preset=None
     return index_path
 
 
+def write_diskann_leann_index(dirpath: Path, name: str, emb: np.ndarray, preset=None, corpus=None, metric="mips", R=32,
+                              n_chunks=None, partition=True, weight_seed=0, device=None):
+    """Lays out what LeannSearcher + the DiskANN searcher expect: <name>_pq_pivots.bin, _pq_compressed.bin, _disk.index
+    (+ partition pair), <name>.leann.meta.json (+ token sidecars).  Returns (index_path, build artefacts)."""
+    from .vamana_build import build_diskann_index
+
+    dirpath.mkdir(parents=True, exist_ok=True)
+    index_path = dirpath / f"{name}.leann"
+    art = build_diskann_index(dirpath, name, emb, metric=metric, R=R, n_chunks=n_chunks, partition=partition, device=device)
+    meta = {"version": "1.0", "backend_name": "diskann_b200", "embedding_model": preset.name if preset else "none",
+            "dimensions": int(emb.shape[1]), "backend_kwargs": {"distance_metric": metric, "graph_degree": R},
+            "embedding_mode": "sentence-transformers", "b200_synthetic_weights": True, "b200_weight_seed": weight_seed}
+    (dirpath / f"{name}.leann.meta.json").write_text(json.dumps(meta))
+    if corpus is not None:
+        np.save(dirpath / f"{name}.leann.tokens.npy", corpus.tokens)
+        np.save(dirpath / f"{name}.leann.tokoffsets.npy", corpus.offsets)
+    return index_path, art
+
+
 def recall_at_k(I, gt):
     return float(np.mean([len(set(a.tolist()) & set(b.tolist())) / len(b) for a, b in zip(I, gt)]))
