@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 1024)))
     ap.add_argument("--per-pass", type=int, default=int(os.environ.get("LB2_PER_PASS", 0)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--diskann", action="store_true", help="extra: the DiskANN/Vamana path over the same corpus (adds ~1-2 min of set-up)")
     return ap.parse_args()
 
 
@@ -300,6 +301,14 @@ def run_b200(args):
     except Exception as e:
         stored = {"error": str(e)}
 
+    # ---------------- extra (opt-in): the DiskANN/Vamana path over the same passages and encoder (SURVEY config C4 shape)
+    diskann = None
+    if args.diskann:
+        try:
+            diskann = diskann_extra(W, args, local, flush, k)
+        except Exception as e:
+            diskann = {"error": repr(e)}
+
     out = None
     if rank == 0:
         peaks = {}
@@ -352,7 +361,7 @@ def run_b200(args):
                        "layernorm_share": agg["norm_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None,
                        "encoder_algorithmic_tflops": (agg["n_tokens"] * 0 + _encoder_flops(W, agg)) / (agg["encoder_ms"] / 1e3) / 1e12 if agg["encoder_ms"] else None,
                        "corpus_embed_tflops": W["embed_tflops"],
-                       "call_scope_dedup": call_scope, "stored_vector_mode": stored},
+                       "call_scope_dedup": call_scope, "stored_vector_mode": stored, "diskann": diskann},
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_reference(W, args, max(1, args.ref_queries), 1)
@@ -361,6 +370,65 @@ def run_b200(args):
         dist.destroy_process_group()
     if out is not None:
         emit(REAL_STDOUT, out)
+
+
+def diskann_extra(W, args, local, flush, k):
+    """DiskANN backend in recompute mode (diskann_backend.py:440-447): PQ-only Vamana traversal, then ONE deferred
+    re-rank of the expanded nodes from freshly encoded passages.  Index built by the torch tooling in the reference's
+    partition layout (what is_recompute=True leaves on disk)."""
+    import torch
+    from leann_b200 import capi
+    from leann_b200.tooling import recall_at_k
+    from leann_b200.vamana_build import build_diskann_index
+
+    t0 = time.time()
+    E = W["E"]
+    prefix, g, coords, pq, codes, max_norm = build_diskann_index(W["work"], "bench_da", E.cpu().numpy(), metric="mips", R=32,
+                                                                 partition=True, keep_disk_index=False, device=f"cuda:{local}")
+    t_build = time.time() - t0
+    log(f"diskann index: R=32, {pq.n_chunks} PQ bytes/vector, mean degree {g.degrees().mean():.1f} ({t_build:.1f}s)")
+    del coords
+    idx = capi.DiskannIndex(prefix, "mips", prefix, local)
+    idx.set_passages(W["corpus"].tokens, W["corpus"].offsets)
+    idx.set_encoder(W["preset"].config(), pack_blob(W))
+    if args.per_pass:
+        idx.configure(0, args.per_pass)
+    nq = min(len(W["Q"]), max(args.queries, 4096))
+    dq = torch.from_numpy(W["Q"][:nq]).to(f"cuda:{local}")
+    dD = torch.empty((nq, k), dtype=torch.float32, device=f"cuda:{local}")
+    dI = torch.empty((nq, k), dtype=torch.int64, device=f"cuda:{local}")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {"build_s": t_build, "graph_degree": 32, "pq_bytes_per_vector": pq.n_chunks, "queries": nq}
+    hbm_peak = (json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs") if (ROOT / "MEASURED_PEAKS.json").exists() else None) or 6650.0
+    for name, p in (("recompute", capi.make_diskann_params(args.ef, max(1, args.beam), recompute_embeddings=True)),
+                    ("recompute_L128", capi.make_diskann_params(2 * args.ef, max(1, args.beam), recompute_embeddings=True)),
+                    ("pq_traversal_only", capi.make_diskann_params(args.ef, max(1, args.beam), recompute_embeddings=False, skip_search_reorder=True))):
+        idx.search_device(dq.data_ptr(), nq, k, dD.data_ptr(), dI.data_ptr(), p)
+        flush.fill_(3)
+        torch.cuda.synchronize()
+        ev0.record()
+        idx.search_device(dq.data_ptr(), nq, k, dD.data_ptr(), dI.data_ptr(), p)
+        ev1.record()
+        torch.cuda.synchronize()
+        sec = ev0.elapsed_time(ev1) / 1e3
+        st = idx.last_stats
+        r = {"value": nq / sec, "unit": "queries/s", "ms": sec * 1e3, "recall_at_10": recall_at_k(dI.cpu().numpy(), W["gt"][:nq]),
+             "expansions_per_query": st.n_requested / nq, "pq_comparisons_per_query": st.ndis / nq,
+             "recomputed_per_query": st.n_recomputed / nq, "encoder_share": st.encoder_ms / st.gpu_ms if st.gpu_ms else None}
+        if name == "pq_traversal_only":
+            # algorithmic bytes: per expansion one adjacency row (4R) + R/8 visited; per compared node its PQ code (n_chunks B)
+            # + n_chunks 4-byte table look-ups (L2-resident) are not counted as HBM traffic
+            byts = st.n_requested * (4 * 32 + 4) + st.ndis * pq.n_chunks
+            r["roofline"] = {"bound": "hbm", "kernel": "vamana_search_kernel (persistent)", "achieved": byts / sec / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": byts / sec / 1e9 / hbm_peak}
+        res[name] = r
+    idx.close()
+    return res
+
+
+def pack_blob(W):
+    from leann_b200 import synth
+    return synth.pack_weights(W["preset"], W["weights"])
 
 
 def _encoder_flops(W, agg):
