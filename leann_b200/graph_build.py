@@ -113,6 +113,43 @@ def _knn_ivf(x: torch.Tensor, k: int, metric_ip: bool, n_clusters: int | None = 
 
 
 @torch.no_grad()
+def _refine_knn(x: torch.Tensor, idx: torch.Tensor, dist: torch.Tensor, metric_ip: bool, rounds: int = 2, fan: int = 16,
+                block: int = 4096) -> tuple[torch.Tensor, torch.Tensor]:
+    """NN-descent style repair of approximate kNN lists: a node's candidates are the lists of its `fan` nearest
+    current neighbours ("a neighbour of a neighbour is likely a neighbour"), scored exactly and merged with the current
+    list.  One round reads fan*k rows of x per node — seconds at 10 M points — and lifts the recall of the
+    partition-restricted lists of _knn_ivf, whose misses are the true neighbours that fell into unprobed cells."""
+    n, k = idx.shape
+    xs = x.half()
+    sq = (x * x).sum(1)
+    for _ in range(rounds):
+        new_idx = torch.empty_like(idx)
+        new_dist = torch.empty_like(dist)
+        for b0 in range(0, n, block):
+            b1 = min(n, b0 + block)
+            cur = idx[b0:b1]                                   # [B, k]
+            nb = cur[:, :fan].clamp(min=0)
+            cand = idx[nb.reshape(-1)].reshape(b1 - b0, -1)    # [B, fan*k]
+            cand = torch.cat([cur, cand], 1)
+            me = torch.arange(b0, b1, device=x.device)[:, None]
+            cand = torch.where(cand == me, torch.full_like(cand, -1), cand)
+            cand, _ = torch.sort(cand, dim=1)
+            dup = torch.zeros_like(cand, dtype=torch.bool)
+            dup[:, 1:] = cand[:, 1:] == cand[:, :-1]
+            bad = dup | (cand < 0)
+            cc = cand.clamp(min=0)
+            ip = torch.bmm(xs[cc], xs[b0:b1].unsqueeze(2)).squeeze(2).float()   # [B, C]
+            d = -ip if metric_ip else (sq[b0:b1, None] + sq[cc] - 2 * ip)
+            d = torch.where(bad, torch.full_like(d, float("inf")), d)
+            dv, di = torch.topk(d, k, dim=1, largest=False)
+            sel = torch.gather(cand, 1, di)
+            new_idx[b0:b1] = torch.where(torch.isinf(dv), torch.full_like(sel, -1), sel)
+            new_dist[b0:b1] = dv
+        idx, dist = new_idx, new_dist
+    return idx, dist
+
+
+@torch.no_grad()
 def _heuristic_prune(x: torch.Tensor, cand: torch.Tensor, cdist: torch.Tensor, keep: int, metric_ip: bool,
                      fill: bool, alpha: float = 1.0, block: int = 8192) -> torch.Tensor:
     """HNSW neighbour selection over candidates sorted by distance (padding = -1 / +inf at the end);
@@ -201,7 +238,7 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
 @torch.no_grad()
 def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
                      knn_factor: float = 1.5, n_scales: int = 2, alpha: float = 1.0, union_factor: int = 2,
-                     ivf_threshold: int = 2_500_000, verbose: bool = False) -> CSRGraph:
+                     ivf_threshold: int = 2_500_000, ivf_refine_rounds: int = 2, verbose: bool = False) -> CSRGraph:
     metric_ip = metric.lower() in ("mips", "cosine", "ip")
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
     x = emb if isinstance(emb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(emb, np.float32))
@@ -225,6 +262,7 @@ def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, 
             # supply the long links a pure kNN graph lacks.
             if nm > ivf_threshold:  # brute force is O(n^2): partition-restricted search beyond a few million points
                 ci, cd = _knn_ivf(xm, int(cap * knn_factor), metric_ip)
+                ci, cd = _refine_knn(xm, ci, cd, metric_ip, rounds=ivf_refine_rounds)
             else:
                 ci, cd = _knn(xm, xm, int(cap * knn_factor), metric_ip, torch.arange(nm, device=dev))
             cis, cds = [ci], [cd]

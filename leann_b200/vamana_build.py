@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import diskann_format as dfmt
-from .graph_build import _add_reverse_and_cap, _heuristic_prune, _knn, _knn_ivf
+from .graph_build import _add_reverse_and_cap, _heuristic_prune, _knn, _knn_ivf, _refine_knn
 
 
 @torch.no_grad()
@@ -28,6 +28,7 @@ def build_vamana_graph(coords, R: int = 32, alpha: float = 1.2, seed: int = 1234
         return dfmt.VamanaGraph(np.full((n, R), -1, np.int32), 0)
     if n > ivf_threshold:
         ci, cd = _knn_ivf(x, int(R * knn_factor), False)
+        ci, cd = _refine_knn(x, ci, cd, False)
     else:
         ci, cd = _knn(x, x, int(R * knn_factor), False, torch.arange(n, device=dev))
     cis, cds = [ci], [cd]

@@ -25,19 +25,24 @@ gt = torch.topk(torch.from_numpy(Q).cuda() @ E.T, 10, dim=1).indices.cpu().numpy
 samp = torch.randperm(N, device="cuda")[:4096]
 ex = torch.topk(E[samp] @ E.T, 49, dim=1).indices[:, 1:]
 orig = graph_build._knn_ivf
-for probes in (0, 12, 32):
+for probes, rounds in ((12, 0), (12, 1), (12, 2), (12, 3), (6, 3)):
     if probes:
         graph_build._knn_ivf = (lambda x, k, ip, _p=probes: orig(x, k, ip, n_probe=_p))
-        ci, _ = graph_build._knn_ivf(E, 48, True)
+        t = time.time()
+        ci, cd = graph_build._knn_ivf(E, 48, True)
+        torch.cuda.synchronize(); t1 = time.time()
+        ci, cd = graph_build._refine_knn(E, ci, cd, True, rounds=rounds)
+        torch.cuda.synchronize(); t2 = time.time()
         hit = (ci[samp][:, :, None] == ex[:, None, :]).any(2).float().mean().item()
-        print(f"n_probe={probes}: candidate-list recall vs exact 48-NN = {hit:.4f}", flush=True)
+        print(f"n_probe={probes} refine rounds={rounds}: candidate-list recall vs exact 48-NN = {hit:.4f}  (ivf {t1-t:.1f}s, refine {t2-t1:.1f}s)", flush=True)
+        del ci, cd
     t = time.time()
-    g = graph_build.build_hnsw_graph(E, M=32, metric="mips", ivf_threshold=(0 if probes else 1 << 40))
+    g = graph_build.build_hnsw_graph(E, M=32, metric="mips", ivf_threshold=(0 if probes else 1 << 40), ivf_refine_rounds=rounds)
     bt = time.time() - t
     f = work / "g.index"; csr.write_compact_index(str(f), g)
     idx = capi.Index(str(f), 0); idx.set_vectors_device(E.data_ptr())
     for ef in (64, 128):
         D, I = idx.search(Q, 10, capi.make_params(ef, recompute=False))
         nd, nh = idx.last_query_stats(len(Q))
-        print(f"{'exact' if not probes else 'ivf n_probe=%d' % probes} build {bt:.0f}s ef={ef}: recall {recall_at_k(I, gt):.4f} ndis {nd.mean():.0f} nhops {nh.mean():.0f}", flush=True)
+        print(f"{'exact' if not probes else 'ivf n_probe=%d refine=%d' % (probes, rounds)} build {bt:.0f}s ef={ef}: recall {recall_at_k(I, gt):.4f} ndis {nd.mean():.0f} nhops {nh.mean():.0f}", flush=True)
     idx.close()
