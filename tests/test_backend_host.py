@@ -92,3 +92,47 @@ def test_registers_into_the_real_leann_registry_when_leann_is_importable():
     env = dict(os.environ, PYTHONPATH=core + os.pathsep + str(__import__('pathlib').Path(__file__).resolve().parents[1]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+# ---------------------------------------------------------------- DiskANN plugin (diskann_b200)
+def test_diskann_backend_registered_and_constructor_errors(tmp_path):
+    from leann_b200 import diskann_backend as db
+    fac = leann_b200.BACKEND_REGISTRY["diskann_b200"]
+    assert issubclass(fac, interface.LeannBackendFactoryInterface) and callable(fac.searcher) and callable(fac.builder)
+    with pytest.raises(FileNotFoundError, match="metadata file not found"):
+        db.B200DiskannSearcher(str(tmp_path / "idx.leann"))
+    (tmp_path / "idx.leann.meta.json").write_text(json.dumps({"dimensions": 16, "backend_kwargs": {"distance_metric": "hamming"}}))
+    with pytest.raises(ValueError, match="Unsupported distance_metric"):
+        db.B200DiskannSearcher(str(tmp_path / "idx.leann"))
+    (tmp_path / "idx.leann.meta.json").write_text(json.dumps({"dimensions": 16, "embedding_model": "m"}))
+    with pytest.raises(FileNotFoundError, match="DiskANN index files not found"):
+        db.B200DiskannSearcher(str(tmp_path / "idx.leann"))
+
+
+def test_diskann_builder_writes_the_reference_file_set_and_search_fails_loudly_without_gpu(tmp_path):
+    """is_recompute=True leaves the partition layout and drops _disk.index, like DiskannBuilder + _safe_cleanup_after_partition
+    (diskann_backend.py:128-190, 268-291); without a GPU the searcher raises instead of falling back to anything."""
+    import torch
+    from leann_b200 import diskann_backend as db
+    from leann_b200 import diskann_format as dfmt
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((600, 16)).astype(np.float32)
+    ids = [str(i) for i in range(len(data))]
+    b = db.B200DiskannBackend.builder(distance_metric="mips", graph_degree=8, pq_chunks=4)
+    b.build(data, ids, str(tmp_path / "docs.leann"), is_recompute=True)
+    files = dfmt.index_files(str(tmp_path / "docs"))
+    assert files["_pq_pivots.bin"] and files["_pq_compressed.bin"] and files["_disk.index_medoids.bin"]
+    assert files["_partition.bin"] and files["_disk_graph.index"] and files["_disk.index_max_base_norm.bin"]
+    assert not files["_disk.index"]
+    with pytest.raises(ValueError, match="decimal strings"):
+        b.build(data, ["a"] * len(data), str(tmp_path / "bad.leann"))
+    (tmp_path / "docs.leann.meta.json").write_text(json.dumps({"dimensions": 16, "embedding_model": "synthetic/tiny-bert",
+                                                                "backend_kwargs": {"distance_metric": "mips"}}))
+    s = db.B200DiskannBackend.searcher(str(tmp_path / "docs.leann"))
+    assert s._partition_prefix.endswith("docs")
+    q = rng.standard_normal((2, 16)).astype(np.float32)
+    with pytest.raises(ValueError, match="zmq_port must be provided"):
+        s.search(q, 5, recompute_embeddings=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device|no CPU path"):
+            s.search(q, 5, recompute_embeddings=False, skip_search_reorder=True)
