@@ -113,12 +113,14 @@ def _knn_ivf(x: torch.Tensor, k: int, metric_ip: bool, n_clusters: int | None = 
 
 
 @torch.no_grad()
-def _refine_knn(x: torch.Tensor, idx: torch.Tensor, dist: torch.Tensor, metric_ip: bool, rounds: int = 2, fan: int = 16,
+def _refine_knn(x: torch.Tensor, idx: torch.Tensor, dist: torch.Tensor, metric_ip: bool, rounds: int = 6, fan: int = 24,
                 block: int = 4096) -> tuple[torch.Tensor, torch.Tensor]:
     """NN-descent style repair of approximate kNN lists: a node's candidates are the lists of its `fan` nearest
     current neighbours ("a neighbour of a neighbour is likely a neighbour"), scored exactly and merged with the current
     list.  One round reads fan*k rows of x per node — seconds at 10 M points — and lifts the recall of the
-    partition-restricted lists of _knn_ivf, whose misses are the true neighbours that fell into unprobed cells."""
+    partition-restricted lists of _knn_ivf, whose misses are the true neighbours that fell into unprobed cells
+    (1 M points, 12 probes: list recall 0.41 -> 0.49 -> 0.58 -> 0.63 over three rounds at fan 16, search recall@10
+    0.870 -> 0.911 against 0.936 with exact lists; profiles/r01e_ivf_refine_recall_1m.log)."""
     n, k = idx.shape
     xs = x.half()
     sq = (x * x).sum(1)
@@ -238,7 +240,7 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
 @torch.no_grad()
 def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
                      knn_factor: float = 1.5, n_scales: int = 2, alpha: float = 1.0, union_factor: int = 2,
-                     ivf_threshold: int = 2_500_000, ivf_refine_rounds: int = 2, verbose: bool = False) -> CSRGraph:
+                     ivf_threshold: int = 2_500_000, ivf_refine_rounds: int = 6, verbose: bool = False) -> CSRGraph:
     metric_ip = metric.lower() in ("mips", "cosine", "ip")
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
     x = emb if isinstance(emb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(emb, np.float32))
