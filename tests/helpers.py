@@ -20,3 +20,21 @@ def golden_key(tag, ef, beam, batch, cr, k):
 
 
 from leann_b200.tooling import open_encoder_only, recall_at_k, stub_graph, write_leann_index  # noqa: E402,F401
+
+
+VAMANA_GOLDEN_CASES = [(64, 1, 10), (32, 4, 5), (16, 2, 10), (100, 2, 10)]  # keep in sync with tests/golden/make_vamana_golden.py
+
+
+def load_vamana_golden(golden_dir, metric):
+    """The committed DiskANN-format fixture, read back with the format readers (not the builder)."""
+    from leann_b200 import diskann_format as dfmt
+
+    prefix = str(golden_dir / f"vamana_small_{metric}")
+    coords, g = dfmt.read_disk_index(prefix + "_disk.index")
+    pq = dfmt.read_pq_pivots(prefix + "_pq_pivots.bin")
+    codes = dfmt.read_bin(prefix + "_pq_compressed.bin", np.uint8)
+    mx = float(dfmt.read_bin(prefix + "_disk.index_max_base_norm.bin", np.float32)[0, 0]) if metric == "mips" else 0.0
+    g.medoid = int(dfmt.read_bin(prefix + "_disk.index_medoids.bin", np.uint32)[0, 0])
+    return dict(prefix=prefix, g=g, coords=coords, pq=pq, codes=codes, max_norm=mx,
+                emb=np.load(golden_dir / "vamana_small_emb.npy"), q=np.load(golden_dir / "vamana_small_queries.npy"),
+                exp=np.load(golden_dir / "vamana_small_expected.npz"))

@@ -64,6 +64,30 @@ def test_stored_coordinates_match_oracle_bit_for_bit(lib, cuda_ok, tmp_path, met
     idx.close()
 
 
+@pytest.mark.parametrize("metric", ["mips", "l2"])
+def test_committed_goldens(lib, cuda_ok, golden_dir, metric):
+    """Standard and partition layouts of the committed fixture against the committed oracle outputs."""
+    from helpers import VAMANA_GOLDEN_CASES, load_vamana_golden
+    G = load_vamana_golden(golden_dir, metric)
+    std = capi.DiskannIndex(G["prefix"], metric)
+    part = capi.DiskannIndex(G["prefix"], metric, G["prefix"])
+    for L, beam, k in VAMANA_GOLDEN_CASES:
+        for idx, mode, p in ((std, "stored", capi.make_diskann_params(L, beam, recompute_embeddings=False)),
+                             (std, "pq", capi.make_diskann_params(L, beam, recompute_embeddings=False, skip_search_reorder=True)),
+                             (part, "pq", capi.make_diskann_params(L, beam, recompute_embeddings=False, skip_search_reorder=True))):
+            key = f"{metric}_L{L}_b{beam}_k{k}_{mode}"
+            D, I = idx.search(G["q"], k, p)
+            assert np.array_equal(I, G["exp"][key + "_I"]) and np.array_equal(D, G["exp"][key + "_D"]), key
+            w = G["exp"][key + "_full"].shape[1]
+            ids, n_full = idx.last_expansions(len(G["q"]), w)
+            assert np.array_equal(n_full, G["exp"][key + "_nfull"])
+            m = np.arange(w)[None, :] < n_full[:, None]
+            assert np.array_equal(ids[m], G["exp"][key + "_full"][m]), key
+            cmps, hops = idx.last_query_stats(len(G["q"]))
+            assert np.array_equal(cmps, G["exp"][key + "_cmps"]) and np.array_equal(hops, G["exp"][key + "_hops"])
+    std.close(); part.close()
+
+
 def test_two_waves_and_edge_cases(lib, cuda_ok, tmp_path):
     emb = rows(3000, 24, 5)
     prefix, g, coords, pq, codes, max_norm = build_diskann_index(tmp_path, "w", emb, metric="l2", R=16, n_chunks=8, partition=False)

@@ -134,6 +134,39 @@ def test_oracle_search_finds_true_neighbours(tmp_path, metric):
     assert info["n_full"].min() >= 10 and (info["n_ios"] == info["n_full"]).all()
 
 
+@needs_ref
+@pytest.mark.parametrize("metric", ["mips", "l2"])
+def test_reference_pq_reads_the_committed_fixture(golden_dir, metric):
+    """The reference's own load_pq_centroid_bin / populate_chunk_distances / pq_dist_lookup on the committed files."""
+    from helpers import load_vamana_golden
+    G = load_vamana_golden(golden_dir, metric)
+    ref = DiskannPrimitives()
+    table = ref.pq_load(G["prefix"] + "_pq_pivots.bin", G["pq"].n_chunks)
+    o = VamanaOracle(G["g"], G["pq"], G["codes"], metric, G["max_norm"])
+    q = np.zeros(G["pq"].ndims, np.float32)
+    q[: G["q"].shape[1]] = G["q"][0]
+    qa, la = ref.lut(table, q, G["pq"].n_chunks)
+    qb, lb = o.lut(q)
+    assert np.array_equal(la, lb)
+    ids = np.arange(0, 1200, 7)
+    assert np.array_equal(ref.pq_dists(la, ids, G["codes"]), o.pq_dists(lb, ids))
+
+
+@pytest.mark.parametrize("metric", ["mips", "l2"])
+def test_oracle_reproduces_committed_goldens(golden_dir, metric):
+    from helpers import VAMANA_GOLDEN_CASES, load_vamana_golden
+    G = load_vamana_golden(golden_dir, metric)
+    o = VamanaOracle(G["g"], G["pq"], G["codes"], metric, G["max_norm"])
+    for L, beam, k in VAMANA_GOLDEN_CASES:
+        for mode, kw in (("stored", dict(coords=G["coords"])), ("deferred", dict(emb=G["emb"])), ("pq", dict(skip_search_reorder=True))):
+            D, I, info = o.search(G["q"], k, L=L, beam_width=beam, **kw)
+            key = f"{metric}_L{L}_b{beam}_k{k}_{mode}"
+            assert np.array_equal(I, G["exp"][key + "_I"]) and np.array_equal(D, G["exp"][key + "_D"]), key
+            assert np.array_equal(info["n_full"], G["exp"][key + "_nfull"]) and np.array_equal(info["cmps"], G["exp"][key + "_cmps"])
+            w = G["exp"][key + "_full"].shape[1]
+            assert np.array_equal(info["full_ids"][:, :w], G["exp"][key + "_full"]), key
+
+
 def test_vamana_builder_degree_and_connectivity():
     x = unit_rows(2000, 24, 4)
     g = build_vamana_graph(x, R=16, device="cpu")
