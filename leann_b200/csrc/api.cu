@@ -507,7 +507,8 @@ bool ensure_vamana_work(lb2_index* x, int64_t wave, int L, int beam, int cap_ful
     }
     if (!w.next_query && (!dev_alloc(&w.next_query, 1) || !dev_alloc(&w.error_flag, 1) || !dev_alloc(&w.claim, 1))) return false;
     w.L = L; w.beam = beam; w.cap_full = x->vcap_full;
-    const int slots = vamana_search_slots(w, x->num_sms);
+    vamana_plan(v, w, x->num_sms);
+    const int slots = w.slots;
     w.vis_words = ((v.n + 31) / 32 + 3) & ~int64_t(3);
     if (x->vcap_slots < slots) {
         if (!dev_alloc(&w.visited, (size_t)slots * (size_t)w.vis_words)) return false;
@@ -640,6 +641,12 @@ int diskann_search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, f
         if (!vamana_launch_rerank(st, v, w)) return LB2_ERR_CUDA;
         launches++;
         x->v_last_wave = wq;
+        if (stats && (nq > wave)) {  // several waves reuse n_full: read it before the next wave overwrites it
+            std::vector<int> nf((size_t)wq);
+            cudaMemcpyAsync(nf.data(), w.n_full, wq * sizeof(int), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            for (int64_t i = 0; i < wq; i++) n_requested += nf[i];
+        }
     }
     cudaEventRecord(x->ev_total.get(), st);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -655,7 +662,7 @@ int diskann_search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, f
         cudaMemcpy(a.data(), x->d_qndis, nq * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaMemcpy(b.data(), x->d_qnhops, nq * sizeof(long long), cudaMemcpyDeviceToHost);
         for (int64_t i = 0; i < nq; i++) { stats->ndis += a[i]; stats->nhops += b[i]; }
-        if (nq <= VAM_WAVE) {
+        if (nq <= wave) {
             std::vector<int> nf((size_t)nq);
             cudaMemcpy(nf.data(), w.n_full, nq * sizeof(int), cudaMemcpyDeviceToHost);
             for (int64_t i = 0; i < nq; i++) n_requested += nf[i];

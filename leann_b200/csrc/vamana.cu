@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace lb2 {
 
@@ -382,15 +383,30 @@ int pick_warps(const VamanaWork& w) {
 
 }  // namespace
 
-int vamana_search_slots(const VamanaWork& w, int num_sms) {
-    const int warps = pick_warps(w);
-    const size_t smem = search_smem(w, warps);
+// Queries in flight = resident warps.  Every in-flight query streams its own n_chunks-KB distance table once per
+// expansion, so the tables of all in-flight queries must stay L2-resident: with one warp per hardware slot
+// (5 920 queries x 268 KB) ncu measured 65 GB of DRAM reads for 2.6 GB of algorithmic bytes at a 2.9 % L2 hit rate
+// (profiles/r01e_traversal_ncu.md).  Cap the table working set at half of the 126 MB L2 and spread the remaining
+// warps over all SMs (narrow blocks) instead of filling a few.
+void vamana_plan(const DevVamana& v, VamanaWork& w, int num_sms) {
+    int warps = pick_warps(w);
+    size_t smem = search_smem(w, warps);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(vamana_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int blocks = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, vamana_search_kernel, warps * 32, smem) != cudaSuccess || blocks < 1)
         blocks = 1;
-    return num_sms * blocks * warps;
+    long long slots = (long long)num_sms * blocks * warps;
+    const long long lut_bytes = (long long)v.n_chunks * 256 * (long long)sizeof(float);
+    long long budget_mb = 64;
+    if (const char* e = getenv("LB2_VAMANA_L2_MB")) budget_mb = std::max(1, atoi(e));  // tuning knob for experiments
+    const long long cap = std::max<long long>(num_sms, (budget_mb << 20) / lut_bytes);
+    if (cap < slots) {
+        while (warps > 1 && cap / warps < 2 * num_sms) warps >>= 1;  // at least two blocks per SM before widening blocks
+        slots = std::max<long long>(1, cap / warps) * warps;
+    }
+    w.warps = warps;
+    w.slots = (int)slots;
 }
 
 bool vamana_launch_prepare(cudaStream_t s, const DevVamana& v, const VamanaWork& w) {
@@ -410,7 +426,7 @@ bool vamana_launch_prepare(cudaStream_t s, const DevVamana& v, const VamanaWork&
 
 bool vamana_launch_search(cudaStream_t s, const DevVamana& v, const VamanaWork& w, int num_sms) {
     if (w.nq == 0) return true;
-    const int warps = pick_warps(w);
+    const int warps = w.warps;
     const size_t smem = search_smem(w, warps);
     if (smem > 227 * 1024) { set_error("complexity L=%d needs %zu bytes of shared memory per query", w.L, smem); return false; }
     if (smem > 48 * 1024)

@@ -42,6 +42,7 @@ struct VamanaWork {
     uint32_t* visited = nullptr;     // [slots, vis_words]
     int64_t vis_words = 0;
     int slots = 0;
+    int warps = 8;                   // warps per block of the traversal kernel
     uint32_t* full_ids = nullptr;    // [nq, cap_full] expanded nodes in expansion order (full_retset)
     float* full_dist = nullptr;      // [nq, cap_full]
     int* n_full = nullptr;           // [nq]
@@ -63,7 +64,7 @@ struct VamanaWork {
     int64_t* outI = nullptr;
 };
 
-int vamana_search_slots(const VamanaWork& w, int num_sms);  // resident warps of the traversal kernel
+void vamana_plan(const DevVamana& v, VamanaWork& w, int num_sms);  // sets w.slots (queries in flight, one warp each) and w.warps
 bool vamana_launch_prepare(cudaStream_t s, const DevVamana& v, const VamanaWork& w);
 bool vamana_launch_search(cudaStream_t s, const DevVamana& v, const VamanaWork& w, int num_sms);
 bool vamana_launch_collect(cudaStream_t s, const DevVamana& v, const VamanaWork& w);
