@@ -276,6 +276,7 @@ def run_b200(args):
     stored = None
     try:
         idx.set_vectors_device(W["E"].data_ptr())
+        idx.configure(148 * 32, 0)  # stored-vector mode wants every warp slot (the recompute arm above ran with --slots)
         nst = min(len(W["Q"]), 8192)
         dqs = torch.from_numpy(W["Q"][:nst]).to(f"cuda:{local}")
         dDs = torch.empty((nst, k), dtype=torch.float32, device=f"cuda:{local}")

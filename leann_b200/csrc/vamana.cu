@@ -383,11 +383,13 @@ int pick_warps(const VamanaWork& w) {
 
 }  // namespace
 
-// Queries in flight = resident warps.  Every in-flight query streams its own n_chunks-KB distance table once per
-// expansion, so the tables of all in-flight queries must stay L2-resident: with one warp per hardware slot
-// (5 920 queries x 268 KB) ncu measured 65 GB of DRAM reads for 2.6 GB of algorithmic bytes at a 2.9 % L2 hit rate
-// (profiles/r01e_traversal_ncu.md).  Cap the table working set at half of the 126 MB L2 and spread the remaining
-// warps over all SMs (narrow blocks) instead of filling a few.
+// Queries in flight = resident warps, one query per warp.  Every in-flight query streams its own n_chunks-KB distance
+// table once per expansion; with every hardware slot occupied (5 920 queries x 154-268 KB) the tables thrash the L2 and
+// ncu shows 65 GB of DRAM reads for 2.6 GB of algorithmic bytes (profiles/r01e_traversal_ncu.md).  Capping the
+// in-flight tables to an L2-sized budget was measured and is SLOWER (1 M points, 154-byte codes: 64 MB -> 2.5e5 q/s,
+// 128 MB -> 2.8e5, no cap -> 4.9e5; profiles/r01e_vamana_l2_budget_sweep.log): the kernel is bound by the latency of
+// its dependent gathers, and thousands of warps hide it better than L2 hits do.  The cap therefore stays off unless
+// LB2_VAMANA_L2_MB is set; the real fix (table in shared memory, one CTA per query) is listed in DESIGN.md section 7.
 void vamana_plan(const DevVamana& v, VamanaWork& w, int num_sms) {
     int warps = pick_warps(w);
     size_t smem = search_smem(w, warps);
@@ -398,7 +400,7 @@ void vamana_plan(const DevVamana& v, VamanaWork& w, int num_sms) {
         blocks = 1;
     long long slots = (long long)num_sms * blocks * warps;
     const long long lut_bytes = (long long)v.n_chunks * 256 * (long long)sizeof(float);
-    long long budget_mb = 64;
+    long long budget_mb = 1ll << 40;  // off
     if (const char* e = getenv("LB2_VAMANA_L2_MB")) budget_mb = std::max(1, atoi(e));  // tuning knob for experiments
     const long long cap = std::max<long long>(num_sms, (budget_mb << 20) / lut_bytes);
     if (cap < slots) {
