@@ -389,7 +389,7 @@ int pick_warps(const VamanaWork& w) {
 // in-flight tables to an L2-sized budget was measured and is SLOWER (1 M points, 154-byte codes: 64 MB -> 2.5e5 q/s,
 // 128 MB -> 2.8e5, no cap -> 4.9e5; profiles/r01e_vamana_l2_budget_sweep.log): the kernel is bound by the latency of
 // its dependent gathers, and thousands of warps hide it better than L2 hits do.  The cap therefore stays off unless
-// LB2_VAMANA_L2_MB is set; the real fix (table in shared memory, one CTA per query) is listed in DESIGN.md section 7.
+// LB2_VAMANA_L2_MB is set; DESIGN.md section 7 discusses the shared-memory-table variant.
 void vamana_plan(const DevVamana& v, VamanaWork& w, int num_sms) {
     int warps = pick_warps(w);
     size_t smem = search_smem(w, warps);
