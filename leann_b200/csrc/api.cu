@@ -697,6 +697,10 @@ void lb2_default_params(lb2_search_params* p) {
 
 lb2_index* lb2_open(const char* index_path, int device) {
     if (!index_path) { set_error("index_path is null"); return nullptr; }
+    // the file is parsed and validated first (host work), so a malformed index is reported as such on any machine
+    HostIndex h;
+    std::string err;
+    if (!read_compact_index(index_path, &h, &err)) { set_error("%s: %s", index_path, err.c_str()); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("no CUDA device available: libleann_b200 has no CPU path");
@@ -708,9 +712,6 @@ lb2_index* lb2_open(const char* index_path, int device) {
         set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
         return nullptr;
     }
-    HostIndex h;
-    std::string err;
-    if (!read_compact_index(index_path, &h, &err)) { set_error("%s: %s", index_path, err.c_str()); return nullptr; }
     lb2_index* x = new lb2_index();
     x->device = device;
     if (!use_device(x)) { delete x; return nullptr; }
@@ -928,6 +929,9 @@ void lb2_diskann_default_params(lb2_diskann_params* p) {
 
 lb2_index* lb2_diskann_open(const char* index_prefix, const char* partition_prefix, int metric, int device) {
     if (!index_prefix) { set_error("index_prefix is null"); return nullptr; }
+    VamanaHost h;
+    std::string err;
+    if (!read_diskann_index(index_prefix, partition_prefix, metric, &h, &err)) { set_error("%s", err.c_str()); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("no CUDA device available: libleann_b200 has no CPU path");
@@ -939,9 +943,6 @@ lb2_index* lb2_diskann_open(const char* index_prefix, const char* partition_pref
         set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
         return nullptr;
     }
-    VamanaHost h;
-    std::string err;
-    if (!read_diskann_index(index_prefix, partition_prefix, metric, &h, &err)) { set_error("%s", err.c_str()); return nullptr; }
     lb2_index* x = new lb2_index();
     x->device = device;
     if (!use_device(x)) { delete x; return nullptr; }
