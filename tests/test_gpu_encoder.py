@@ -52,3 +52,40 @@ def test_encode_tokens_equals_encode_ids_and_truncates(lib, cuda_ok):
     t = idx.encode_tokens(long_seq.astype(np.uint16), np.array([0, long_seq.size], np.uint64))
     t2 = idx.encode_tokens(long_seq[: preset.max_pos].astype(np.uint16), np.array([0, preset.max_pos], np.uint64))
     assert np.array_equal(t, t2)  # truncation=True at max_seq_length
+
+
+def test_embedding_server_shim_serves_gpu_embeddings(lib, cuda_ok):
+    """The reference's msgpack/ZMQ protocol answered by the GPU encoder (what an unmodified LEANN client would receive)."""
+    import threading
+    zmq = pytest.importorskip("zmq")
+    msgpack = pytest.importorskip("msgpack")
+    from leann_b200.embedding_server import serve
+    preset = synth.TINY
+    blob = synth.pack_weights(preset, synth.synthetic_weights(preset, 4))
+    tm, corpus = synth.make_corpus(300, preset.vocab_size, seed=31, max_len=preset.max_pos)
+    idx = open_encoder_only(preset, blob, corpus)
+    E = idx.encode_ids(np.arange(corpus.n))
+    stop, ready = threading.Event(), threading.Event()
+    port = 6200 + int(np.random.default_rng().integers(0, 300))
+    th = threading.Thread(target=serve, args=(idx, port), kwargs=dict(distance_metric="mips", model_name=preset.name, shutdown=stop, ready=ready), daemon=True)
+    th.start()
+    assert ready.wait(10)
+    ctx = zmq.Context()
+    s = ctx.socket(zmq.REQ)
+    s.setsockopt(zmq.RCVTIMEO, 20000)
+    s.setsockopt(zmq.LINGER, 0)
+    s.connect(f"tcp://127.0.0.1:{port}")
+    try:
+        ids = [5, 17, 299, 100000]
+        s.send(msgpack.packb([ids, E[3].tolist()]))
+        (dist,) = msgpack.unpackb(s.recv())
+        assert dist[3] == 1e9 and np.allclose(dist[:3], -(E[[5, 17, 299]] @ E[3]), atol=1e-6)
+        s.send(msgpack.packb([[7, 8]]))
+        dims, flat = msgpack.unpackb(s.recv())
+        assert dims == [2, preset.hidden] and np.array_equal(np.asarray(flat, np.float32).reshape(2, -1), E[[7, 8]])
+    finally:
+        stop.set()
+        s.close()
+        ctx.term()
+        th.join(5)
+        idx.close()
