@@ -216,3 +216,29 @@ def test_plugin_searcher_end_to_end(rc):
     assert s.search(qe, 1, zmq_port=port, recompute_embeddings=True)["labels"][0][0] == "33"
     assert s.last_stats["n_recomputed"] > 0
     s.cleanup()
+
+
+def test_bge_base_768d_diskann_recompute(lib, cuda_ok, tmp_path):
+    """Config C4's shape at test size: bge-base architecture (12 layers, 768d, CLS pooling) behind the DiskANN path — 769 stored
+    dimensions (odd), default PQ budget rule, partition layout."""
+    from leann_b200 import diskann_format as dfmt
+    preset = synth.BGE_BASE
+    w = synth.synthetic_weights(preset, 3)
+    blob = synth.pack_weights(preset, w)
+    tm, corpus = synth.make_corpus(700, preset.vocab_size, seed=5, max_len=200)
+    queries = synth.make_queries(tm, 16, seed=6)
+    enc = open_encoder_only(preset, blob, corpus)
+    E = enc.encode_ids(np.arange(corpus.n))
+    Q = enc.encode_tokens(queries.tokens, queries.offsets)
+    enc.close()
+    n_chunks = min(96, dfmt.default_num_chunks(len(E), 769))  # the rule gives dim-many chunks at this tiny size; keep the test light
+    prefix, g, coords, pq, codes, mx = build_diskann_index(tmp_path, "bge", E, metric="mips", R=16, n_chunks=n_chunks, partition=True,
+                                                           keep_disk_index=False)
+    idx = capi.DiskannIndex(prefix, "mips", prefix)
+    assert (idx.dinfo.dim, idx.dinfo.data_dim) == (768, 769)
+    idx.set_passages(corpus.tokens, corpus.offsets)
+    idx.set_encoder(preset.config(), blob)
+    idx.configure(0, 128)
+    o = VamanaOracle(g, pq, codes, "mips", mx)
+    check_same(idx, o, Q, 10, 48, 2, emb=E)
+    idx.close()
