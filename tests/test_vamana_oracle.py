@@ -167,6 +167,58 @@ def test_oracle_reproduces_committed_goldens(golden_dir, metric):
             assert np.array_equal(info["full_ids"][:, :w], G["exp"][key + "_full"]), key
 
 
+def _beam_search_with_reference_primitives(ref, table, G, q, L, beam, k, io_limit=2 ** 32 - 1):
+    """Second, independent transcription of the loop of PQFlashIndex::cached_beam_search (pq_flash_index.cpp:2110-2211,
+    2419-2612, 2761, 2861-2883; L2 metric, skip_search_reorder) driving the REFERENCE's compiled queue and PQ table, so the
+    only non-reference code involved is this loop."""
+    g, codes, n_chunks = G["g"], G["codes"], G["pq"].n_chunks
+    _, lut = ref.lut(table, q, n_chunks)                      # preprocess_query + populate_chunk_distances
+    retset = ref.queue(L)
+    visited = set()
+    med = g.medoid
+    retset.insert(med, float(ref.pq_dists(lut, [med], codes)[0]))
+    visited.add(med)
+    full, cmps, hops, ios = [], 0, 0, 0
+    while retset.has_unexpanded() and ios < io_limit:
+        frontier = []
+        while retset.has_unexpanded() and len(frontier) < beam:
+            frontier.append(retset.closest_unexpanded())
+        if frontier:
+            hops += 1
+        ios += len(frontier)
+        for node, d in frontier:
+            full.append((d, node))
+            nb = g.nbrs[node]
+            nb = nb[nb >= 0]
+            dists = ref.pq_dists(lut, nb, codes)
+            for m, i in enumerate(nb.tolist()):
+                if i not in visited:
+                    visited.add(i)
+                    cmps += 1
+                    retset.insert(i, float(dists[m]))
+    order = sorted(full)                                      # Neighbor::operator< : (distance, id)
+    ids = [i for _, i in order[:k]] + [-1] * max(0, k - len(order))
+    ds = [d for d, _ in order[:k]] + [np.finfo(np.float32).max] * max(0, k - len(order))
+    return np.array(ids), np.array(ds, np.float32), [i for _, i in full], cmps, hops
+
+
+@needs_ref
+def test_search_loop_agrees_with_a_second_transcription_over_reference_primitives(golden_dir):
+    from helpers import load_vamana_golden
+    G = load_vamana_golden(golden_dir, "l2")
+    ref = DiskannPrimitives()
+    table = ref.pq_load(G["prefix"] + "_pq_pivots.bin", G["pq"].n_chunks)
+    o = VamanaOracle(G["g"], G["pq"], G["codes"], "l2", 0.0)
+    for L, beam, k, io_limit in [(64, 1, 10, 2 ** 32 - 1), (16, 4, 10, 2 ** 32 - 1), (8, 3, 20, 2 ** 32 - 1), (32, 2, 5, 9)]:
+        D, I, info = o.search(G["q"], k, L=L, beam_width=beam, skip_search_reorder=True, io_limit=io_limit)
+        for qi in range(len(G["q"])):
+            ids, ds, full, cmps, hops = _beam_search_with_reference_primitives(ref, table, G, G["q"][qi], L, beam, k, io_limit)
+            n = info["n_full"][qi]
+            assert info["full_ids"][qi, :n].tolist() == full, (L, beam, qi)
+            assert (info["cmps"][qi], info["n_hops"][qi]) == (cmps, hops)
+            assert np.array_equal(I[qi], ids) and np.array_equal(D[qi], ds)
+
+
 def test_vamana_builder_degree_and_connectivity():
     x = unit_rows(2000, 24, 4)
     g = build_vamana_graph(x, R=16, device="cpu")
