@@ -79,6 +79,19 @@ class B200HnswBuilder(LeannBackendBuilderInterface):
         write_compact_index(str(path.parent / f"{path.stem}.index"), g)
 
 
+class _InProcessRecomputeStage:
+    """What LeannSearcher.cleanup() / BaseSearcher.__del__ look for (leann-core api.py:798-806, searcher_base.py:194-197):
+    an ``embedding_server_manager`` with ``stop_server()``.  The reference stops its embedding-server process there; here
+    the "server" is the GPU-resident recompute stage, so stopping it releases the device handle (graph, passages, encoder).
+    The next search re-opens it, like the reference re-spawns its server."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def stop_server(self):
+        self._owner._release_device()
+
+
 class _B200SearcherBase(LeannBackendSearcherInterface):
     """What ``BaseSearcher`` gives the reference's searchers (leann-core/src/leann/searcher_base.py:18-160), with the
     embedding *server* replaced by the in-process GPU recompute stage."""
@@ -101,6 +114,21 @@ class _B200SearcherBase(LeannBackendSearcherInterface):
         self._tokenizer = None
         self._recompute_ready = False
         self.preset: synth.ModelPreset | None = None
+        self._index = None
+        self.embedding_server_manager = _InProcessRecomputeStage(self)
+
+    def _open_index(self) -> None:  # subclasses: create self._index
+        raise NotImplementedError
+
+    def _ensure_open(self) -> None:
+        if self._index is None:
+            self._open_index()
+
+    def _release_device(self) -> None:
+        if self._index is not None:
+            self._index.close()
+            self._index = None
+        self._recompute_ready = False
 
     # ------------------------------------------------------------------ helpers
     def _load_meta(self) -> dict[str, Any]:
@@ -133,6 +161,7 @@ class _B200SearcherBase(LeannBackendSearcherInterface):
         return weights_from_hf(hf, name)
 
     def _attach_recompute_stage(self):
+        self._ensure_open()
         if self._recompute_ready:
             return
         tok_f, off_f = self._sidecar("tokens.npy"), self._sidecar("tokoffsets.npy")
@@ -161,7 +190,7 @@ class _B200SearcherBase(LeannBackendSearcherInterface):
                                 zmq_port: Optional[int] = None) -> np.ndarray:
         """(1, D) float32 embedding of the query with the SAME GPU encoder as the passages.
         ``query`` is a string (needs the model's WordPiece tokenizer on disk) or an array of token ids."""
-        self._attach_recompute_stage()
+        self._attach_recompute_stage()  # (re)opens the handle if cleanup() released it
         if isinstance(query, str):
             if self._tokenizer is None:
                 try:
@@ -179,10 +208,10 @@ class _B200SearcherBase(LeannBackendSearcherInterface):
 
     @property
     def last_stats(self) -> dict[str, Any]:
-        return self._index.last_stats.as_dict()
+        return self._index.last_stats.as_dict() if self._index is not None else {}
 
     def cleanup(self):
-        self._index.close()
+        self._release_device()
 
 
 class B200HnswSearcher(_B200SearcherBase):
@@ -198,18 +227,25 @@ class B200HnswSearcher(_B200SearcherBase):
             raise FileNotFoundError(f"HNSW index file not found at {index_file}")
         if not self.is_compact:
             raise RuntimeError("the B200 backend reads compact (CSR) HNSW indexes only")
-        self._index = capi.Index(str(index_file), self.device)
+        self._index_file = str(index_file)
+        self._tuning = {k: kwargs[k] for k in ("slots", "passages_per_pass", "dedup_scope") if kwargs.get(k) is not None}
+        self._open_index()
+
+    def _open_index(self) -> None:
+        self._index = capi.Index(self._index_file, self.device)
         if self._index.info.d != int(self.dimensions):
             raise ValueError(f"index dimension {self._index.info.d} != meta dimensions {self.dimensions}")
-        if kwargs.get("slots") or kwargs.get("passages_per_pass"):
-            self._index.configure(int(kwargs.get("slots", 0)), int(kwargs.get("passages_per_pass", 0)))
-        if kwargs.get("dedup_scope") is not None:  # "hop" (default) | "call"
-            self._index.set_option("dedup_scope", {"hop": 0, "call": 1}[str(kwargs["dedup_scope"])])
+        t = self._tuning
+        if t.get("slots") or t.get("passages_per_pass"):
+            self._index.configure(int(t.get("slots", 0)), int(t.get("passages_per_pass", 0)))
+        if t.get("dedup_scope") is not None:  # "hop" (default) | "call"
+            self._index.set_option("dedup_scope", {"hop": 0, "call": 1}[str(t["dedup_scope"])])
 
     def search(self, query: np.ndarray, top_k: int, zmq_port: Optional[int] = None, complexity: int = 64,
                beam_width: int = 1, prune_ratio: float = 0.0, recompute_embeddings: bool = True,
                pruning_strategy: Literal["global", "local", "proportional"] = "global", batch_size: int = 0,
                **kwargs) -> dict[str, Any]:
+        self._ensure_open()
         if not recompute_embeddings and self.is_pruned and not self._index.info.has_vectors:
             raise RuntimeError("Recompute is required for pruned/compact HNSW index. "
                                "Re-run search with --recompute, or rebuild with --no-recompute and --no-compact.")

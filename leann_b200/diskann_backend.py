@@ -74,27 +74,24 @@ class B200DiskannSearcher(_B200SearcherBase):
         self._partition_prefix = self._index_prefix if graph_f.exists() and part_f.exists() else ""
         if not Path(self._index_prefix + "_pq_compressed.bin").exists():
             raise FileNotFoundError(f"DiskANN index files not found at prefix {self._index_prefix}")
-        self._index = None
         self._current_zmq_port = None
         self._tuning = {k: kwargs[k] for k in ("passages_per_pass",) if kwargs.get(k)}
 
-    def _ensure_index_loaded(self, zmq_port: int):
-        """diskann_backend.py:359-381 reloads the index when the port changes; there is no port here, so the index
-        is loaded once."""
-        if self._index is None:
-            try:
-                self._index = capi.DiskannIndex(self._index_prefix, self.distance_metric, self._partition_prefix, self.device)
-            except capi.Lb2Error as e:
-                raise RuntimeError(str(e)) from e
-            if self._index.dinfo.dim != int(self.dimensions):
-                raise ValueError(f"index dimension {self._index.dinfo.dim} != meta dimensions {self.dimensions}")
-            if self._tuning:
-                self._index.configure(0, int(self._tuning["passages_per_pass"]))
-        self._current_zmq_port = zmq_port
+    def _open_index(self) -> None:
+        try:
+            self._index = capi.DiskannIndex(self._index_prefix, self.distance_metric, self._partition_prefix, self.device)
+        except capi.Lb2Error as e:
+            raise RuntimeError(str(e)) from e
+        if self._index.dinfo.dim != int(self.dimensions):
+            raise ValueError(f"index dimension {self._index.dinfo.dim} != meta dimensions {self.dimensions}")
+        if self._tuning:
+            self._index.configure(0, int(self._tuning["passages_per_pass"]))
 
-    def _attach_recompute_stage(self):
-        self._ensure_index_loaded(self._current_zmq_port or 6666)
-        super()._attach_recompute_stage()
+    def _ensure_index_loaded(self, zmq_port: int):
+        """diskann_backend.py:359-381 loads the index lazily and reloads it when the port changes; there is no port here,
+        so the index is loaded once (and again after cleanup() released it)."""
+        self._ensure_open()
+        self._current_zmq_port = zmq_port
 
     def search(self, query: np.ndarray, top_k: int, complexity: int = 64, beam_width: int = 1, prune_ratio: float = 0.0,
                recompute_embeddings: bool = False,
@@ -125,15 +122,6 @@ class B200DiskannSearcher(_B200SearcherBase):
             raise RuntimeError(str(e)) from e
         string_labels = [[str(int_label) for int_label in batch_labels] for batch_labels in labels]
         return {"labels": string_labels, "distances": distances}
-
-    @property
-    def last_stats(self) -> dict[str, Any]:
-        return self._index.last_stats.as_dict() if self._index is not None else {}
-
-    def cleanup(self):
-        if self._index is not None:
-            self._index.close()
-            self._index = None
 
 
 @register_backend(BACKEND_NAME)

@@ -256,3 +256,9 @@ def test_plugin_searcher_end_to_end(lib, cuda_ok, rc):
     out2 = s.search(rc["Q"][:5], 5, zmq_port=port, prune_ratio=0.3)
     assert out2["labels"] == out["labels"]
     assert s.last_stats["ndis"] > 0
+    # LeannSearcher.cleanup() -> embedding_server_manager.stop_server(): device handle released, next search re-opens it
+    s.embedding_server_manager.stop_server()
+    assert s._index is None and s.last_stats == {}
+    out3 = s.search(rc["Q"][:5], 5, zmq_port=port, complexity=64, recompute_embeddings=True)
+    assert out3["labels"] == out["labels"] and np.array_equal(out3["distances"], out["distances"])
+    s.cleanup()

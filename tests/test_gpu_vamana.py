@@ -215,6 +215,10 @@ def test_plugin_searcher_end_to_end(rc):
     assert np.array_equal(qe[0], rc["E"][33])
     assert s.search(qe, 1, zmq_port=port, recompute_embeddings=True)["labels"][0][0] == "33"
     assert s.last_stats["n_recomputed"] > 0
+    s.embedding_server_manager.stop_server()  # what LeannSearcher.cleanup() calls
+    assert s._index is None
+    again = s.search(rc["Q"][:6], 5, zmq_port=port, complexity=64, beam_width=2, recompute_embeddings=True)
+    assert again["labels"] == out["labels"] and np.array_equal(again["distances"], out["distances"])
     s.cleanup()
 
 
