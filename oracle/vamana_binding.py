@@ -97,6 +97,14 @@ class VamanaOracle:
         return D, I, dict(full_ids=full_ids, full_dists=full_d, n_full=n_full, cmps=stats[:, 0], n_ios=stats[:, 1],
                           n_hops=stats[:, 2])
 
+    def prepare_query(self, q):
+        """(aligned_query_T [data_dim], |q|) as cached_beam_search forms them (pq_flash_index.cpp:1819-1848)."""
+        q = np.ascontiguousarray(q, np.float32)
+        aq = np.zeros(self.data_dim, np.float32)
+        nrm = C.c_float(0)
+        self.lib.vo_prepare_query(C.byref(self.cx), _p(q, C.c_float), _p(aq, C.c_float), C.byref(nrm))
+        return aq, nrm.value
+
     # primitive hooks (pinned against DiskannPrimitives)
     def lut(self, qvec_prepared):
         """qvec_prepared [data_dim] (already normalised / extended) -> (centred query, LUT [n_chunks, 256])."""

@@ -159,6 +159,23 @@ void vo_preprocess_embedding(const vo_index* x, const float* emb, int dim, float
     }
 }
 
+/* ---------------------------------------------------------------- query normalisation: src/pq_flash_index.cpp:1819-1848 */
+void vo_prepare_query(const vo_index* x, const float* query, float* aq /* [data_dim], zero-initialised */, float* query_norm_out) {
+    const int D = x->data_dim;
+    float query_norm = 0;
+    if (x->metric == VO_MIPS || x->metric == VO_COSINE) {
+        const int inherent = x->metric == VO_COSINE ? D : D - 1;
+        /* query_norm += q*q, contracted to an fma by the reference's build flags (see populate_chunk_distances) */
+        for (int i = 0; i < inherent; i++) { aq[i] = query[i]; query_norm = fmaf(query[i], query[i], query_norm); }
+        if (x->metric == VO_MIPS) aq[D - 1] = 0;
+        query_norm = sqrtf(query_norm);
+        for (int i = 0; i < inherent; i++) aq[i] = aq[i] / query_norm;
+    } else {
+        for (int i = 0; i < D; i++) aq[i] = query[i];
+    }
+    *query_norm_out = query_norm;
+}
+
 /* ---------------------------------------------------------------- cached_beam_search: src/pq_flash_index.cpp:1779-2906 */
 typedef struct { uint32_t id; float dist; } vo_nb;
 static int cmp_nb(const void* a, const void* b) {
@@ -187,17 +204,7 @@ int vo_search(const vo_index* x, const float* tables_tr, const float* query, int
     uint32_t* frontier = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(beam_width + 1));
     float* frontier_d = (float*)malloc(sizeof(float) * (size_t)(beam_width + 1));
     float query_norm = 0;
-    /* :1822-1848 */
-    if (x->metric == VO_MIPS || x->metric == VO_COSINE) {
-        const int inherent = x->metric == VO_COSINE ? D : D - 1;
-        /* query_norm += q*q, contracted to an fma by the reference's build flags (see populate_chunk_distances) */
-        for (int i = 0; i < inherent; i++) { aq[i] = query[i]; query_norm = fmaf(query[i], query[i], query_norm); }
-        if (x->metric == VO_MIPS) aq[D - 1] = 0;
-        query_norm = sqrtf(query_norm);
-        for (int i = 0; i < inherent; i++) aq[i] = aq[i] / query_norm;
-    } else {
-        for (int i = 0; i < D; i++) aq[i] = query[i];
-    }
+    vo_prepare_query(x, query, aq, &query_norm);
     (void)dim;
     memcpy(qrot, aq, sizeof(float) * (size_t)D);
     vo_pq_preprocess_query(x, qrot);                           /* :1859 */

@@ -167,7 +167,7 @@ def test_oracle_reproduces_committed_goldens(golden_dir, metric):
             assert np.array_equal(info["full_ids"][:, :w], G["exp"][key + "_full"]), key
 
 
-def _beam_search_with_reference_primitives(ref, table, G, q, L, beam, k, io_limit=2 ** 32 - 1):
+def _beam_search_with_reference_primitives(ref, table, G, q, L, beam, k, io_limit=2 ** 32 - 1, metric="l2", scale=None):
     """Second, independent transcription of the loop of PQFlashIndex::cached_beam_search (pq_flash_index.cpp:2110-2211,
     2419-2612, 2761, 2861-2883; L2 metric, skip_search_reorder) driving the REFERENCE's compiled queue and PQ table, so the
     only non-reference code involved is this loop."""
@@ -198,8 +198,13 @@ def _beam_search_with_reference_primitives(ref, table, G, q, L, beam, k, io_limi
                     retset.insert(i, float(dists[m]))
     order = sorted(full)                                      # Neighbor::operator< : (distance, id)
     ids = [i for _, i in order[:k]] + [-1] * max(0, k - len(order))
-    ds = [d for d, _ in order[:k]] + [np.finfo(np.float32).max] * max(0, k - len(order))
-    return np.array(ids), np.array(ds, np.float32), [i for _, i in full], cmps, hops
+    ds = np.array([d for d, _ in order[:k]], np.float32)
+    if metric == "mips":                                      # :2873-2881
+        ds = -ds
+        if scale is not None:
+            ds = ds * np.float32(scale)
+    ds = np.concatenate([ds, np.full(max(0, k - len(order)), np.finfo(np.float32).max, np.float32)])
+    return np.array(ids), ds, [i for _, i in full], cmps, hops
 
 
 @needs_ref
@@ -216,6 +221,27 @@ def test_search_loop_agrees_with_a_second_transcription_over_reference_primitive
             n = info["n_full"][qi]
             assert info["full_ids"][qi, :n].tolist() == full, (L, beam, qi)
             assert (info["cmps"][qi], info["n_hops"][qi]) == (cmps, hops)
+            assert np.array_equal(I[qi], ids) and np.array_equal(D[qi], ds)
+
+
+@needs_ref
+def test_search_loop_second_transcription_mips_with_query_normalisation(golden_dir):
+    """Same cross-check for the MIPS index: the query is normalised / extended by the oracle's vo_prepare_query, everything
+    after that (centring, table, queue, distances) is the reference's compiled code."""
+    from helpers import load_vamana_golden
+    G = load_vamana_golden(golden_dir, "mips")
+    ref = DiskannPrimitives()
+    table = ref.pq_load(G["prefix"] + "_pq_pivots.bin", G["pq"].n_chunks)
+    o = VamanaOracle(G["g"], G["pq"], G["codes"], "mips", G["max_norm"])
+    for L, beam, k in [(64, 1, 10), (16, 4, 10)]:
+        D, I, info = o.search(G["q"], k, L=L, beam_width=beam, skip_search_reorder=True)
+        for qi in range(len(G["q"])):
+            aq, nrm = o.prepare_query(G["q"][qi])
+            assert abs(nrm - np.linalg.norm(G["q"][qi])) < 1e-5 and aq[-1] == 0 and abs(np.linalg.norm(aq) - 1) < 1e-6
+            scale = np.float32(G["max_norm"]) * np.float32(nrm)
+            ids, ds, full, cmps, hops = _beam_search_with_reference_primitives(ref, table, G, aq, L, beam, k, metric="mips", scale=scale)
+            n = info["n_full"][qi]
+            assert info["full_ids"][qi, :n].tolist() == full and (info["cmps"][qi], info["n_hops"][qi]) == (cmps, hops)
             assert np.array_equal(I[qi], ids) and np.array_equal(D[qi], ds)
 
 
