@@ -6,7 +6,8 @@ import types
 import numpy as np
 import pytest
 
-from leann_b200.embedding_server import LARGE_DISTANCE, handle_request, serve
+from leann_b200.embedding_server import (LARGE_DISTANCE, decode_node_embedding_request, encode_node_embedding_response,
+                                         handle_diskann_request, handle_request, serve)
 
 DIM, N = 8, 20
 TABLE = np.random.default_rng(0).standard_normal((N, DIM)).astype(np.float32)
@@ -70,3 +71,49 @@ def test_zmq_round_trip_like_the_cpp_client():
         s.close()
         ctx.term()
         th.join(5)
+
+
+def _proto_classes():
+    """The two messages of third_party/embedding.proto built with the protobuf runtime's dynamic descriptors (no generated
+    code): the independent codec the hand-written wire format is checked against."""
+    pytest.importorskip("google.protobuf")
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name="embedding_test.proto", package="protoembedding_test", syntax="proto3")
+    req = fd.message_type.add(name="NodeEmbeddingRequest")
+    req.field.add(name="node_ids", number=1, type=descriptor_pb2.FieldDescriptorProto.TYPE_UINT32,
+                  label=descriptor_pb2.FieldDescriptorProto.LABEL_REPEATED)
+    resp = fd.message_type.add(name="NodeEmbeddingResponse")
+    resp.field.add(name="embeddings_data", number=1, type=descriptor_pb2.FieldDescriptorProto.TYPE_BYTES,
+                   label=descriptor_pb2.FieldDescriptorProto.LABEL_OPTIONAL)
+    resp.field.add(name="dimensions", number=2, type=descriptor_pb2.FieldDescriptorProto.TYPE_INT32,
+                   label=descriptor_pb2.FieldDescriptorProto.LABEL_REPEATED)
+    resp.field.add(name="missing_ids", number=3, type=descriptor_pb2.FieldDescriptorProto.TYPE_UINT32,
+                   label=descriptor_pb2.FieldDescriptorProto.LABEL_REPEATED)
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = message_factory.GetMessageClass
+    return get(pool.FindMessageTypeByName("protoembedding_test.NodeEmbeddingRequest")), \
+        get(pool.FindMessageTypeByName("protoembedding_test.NodeEmbeddingResponse"))
+
+
+def test_diskann_protobuf_variant_against_the_protobuf_runtime():
+    Req, Resp = _proto_classes()
+    for ids in ([3], [0, 1, 19], list(range(0, 20, 3)), [2 ** 31 + 5, 7][1:]):
+        raw = Req(node_ids=ids).SerializeToString()
+        assert decode_node_embedding_request(raw) == ids
+        out = Resp()
+        out.ParseFromString(handle_diskann_request(raw, encode_ids=enc_ids, encode_texts=None, n_passages=N))
+        assert list(out.dimensions) == [len(ids), DIM] and not out.missing_ids
+        assert np.array_equal(np.frombuffer(out.embeddings_data, np.float32).reshape(len(ids), DIM), TABLE[ids])
+    r = Resp()
+    r.ParseFromString(encode_node_embedding_response(np.zeros((0, DIM), np.float32), missing=[4, 300]))
+    assert list(r.dimensions) == [0, DIM] and list(r.missing_ids) == [4, 300] and r.embeddings_data == b""
+    with pytest.raises(KeyError):
+        handle_diskann_request(Req(node_ids=[1, 999]).SerializeToString(), encode_ids=enc_ids, encode_texts=None, n_passages=N)
+    # msgpack text fallback (BaseSearcher.compute_query_embedding), and garbage
+    msgpack = pytest.importorskip("msgpack")
+    emb = msgpack.unpackb(handle_diskann_request(msgpack.packb(["ab", "c"]), encode_ids=enc_ids, n_passages=N,
+                                                 encode_texts=lambda ts: np.stack([np.full(DIM, len(t), np.float32) for t in ts])))
+    assert emb == [[2.0] * DIM, [1.0] * DIM]
+    with pytest.raises(RuntimeError, match="Both protobuf and msgpack parsing failed"):
+        handle_diskann_request(b"\xff\xff\xff", encode_ids=enc_ids, encode_texts=None, n_passages=N)
