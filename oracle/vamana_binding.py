@@ -9,7 +9,6 @@
 from __future__ import annotations
 
 import ctypes as C
-from pathlib import Path
 
 import numpy as np
 
