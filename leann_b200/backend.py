@@ -116,6 +116,17 @@ class _B200SearcherBase(LeannBackendSearcherInterface):
         self.preset: synth.ModelPreset | None = None
         self._index = None
         self.embedding_server_manager = _InProcessRecomputeStage(self)
+        # one process per GPU (torchrun): split each call's query batch over the ranks and all_gather the results
+        # (leann_b200/parallel.py).  Off by default: a lone process answers its whole batch like the reference.
+        self._shard_queries = bool(kwargs.get("shard_queries", False))
+
+    def _run_search(self, query: np.ndarray, top_k: int, params):
+        run = lambda qs: self._index.search(np.ascontiguousarray(qs), int(top_k), params)  # noqa: E731
+        if self._shard_queries:
+            from .parallel import sharded_search
+
+            return sharded_search(run, query, int(top_k))
+        return run(query)
 
     def _open_index(self) -> None:  # subclasses: create self._index
         raise NotImplementedError
@@ -272,7 +283,7 @@ class B200HnswSearcher(_B200SearcherBase):
         params = capi.make_params(complexity, beam_width, batch_size, check_rel, prune_ratio, local_prune, send_ratio,
                                   recompute_embeddings)
         try:
-            distances, labels = self._index.search(np.ascontiguousarray(query), int(top_k), params)
+            distances, labels = self._run_search(query, top_k, params)
         except capi.Lb2Error as e:
             if "not implemented" in str(e):
                 raise NotImplementedError(str(e)) from e

@@ -115,7 +115,7 @@ class B200DiskannSearcher(_B200SearcherBase):
             dedup_node_dis=dedup_node_dis, prune_ratio=prune_ratio, batch_recompute=batch_recompute,
             global_pruning=(pruning_strategy != "local"))
         try:
-            distances, labels = self._index.search(np.ascontiguousarray(query), int(top_k), params)
+            distances, labels = self._run_search(query, top_k, params)
         except capi.Lb2Error as e:
             if "not implemented" in str(e):
                 raise NotImplementedError(str(e)) from e

@@ -51,3 +51,69 @@ def test_world2_gloo_sharded_search_matches_single_process():
         D, I, calls, (lo, hi) = ret[r]
         assert np.array_equal(D, expD) and np.array_equal(I, expI)
         assert calls == [hi - lo]  # each rank searched only its own slice
+
+
+def _plugin_worker(rank, world, port, tmp, ret):
+    """Both plugin searchers with shard_queries=True under a 2-rank gloo group; the device handle is a fake that scores
+    from the query values so that every rank can check the gathered result."""
+    import json
+    from pathlib import Path
+
+    from leann_b200 import backend, capi, diskann_backend
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seen = []
+
+    class Fake:
+        def __init__(self, *a, **kw):
+            self.info = type("I", (), dict(d=4, ntotal=100, has_vectors=1))()
+            self.dinfo = type("D", (), dict(dim=4))()
+            self.last_stats = capi.SearchStats()
+
+        def configure(self, *a): pass
+        def set_option(self, *a): pass
+        def close(self): pass
+
+        def search(self, q, k, params):
+            seen.append(len(q))
+            base = q[:, :1]
+            return (base + np.arange(k, dtype=np.float32)[None]), (base.astype(np.int64) + np.arange(k)[None])
+
+    capi.Index = Fake
+    capi.DiskannIndex = Fake
+    d = Path(tmp)
+    meta = {"backend_name": "x", "embedding_model": "synthetic/tiny-bert", "dimensions": 4, "backend_kwargs": {"distance_metric": "l2"},
+            "is_compact": True, "is_pruned": False}
+    out = {}
+    for name, cls, marker in (("h", backend.B200HnswSearcher, "h.index"), ("d", diskann_backend.B200DiskannSearcher, "d_pq_compressed.bin")):
+        if rank == 0:
+            (d / f"{name}.leann.meta.json").write_text(json.dumps(meta))
+            (d / marker).write_bytes(b"x")
+        dist.barrier()
+        s = cls(str(d / f"{name}.leann"), shard_queries=True)
+        assert s.device == rank  # one process per GPU: LOCAL_RANK picks the device
+        q = np.arange(9 * 4, dtype=np.float32).reshape(9, 4)
+        seen.clear()
+        res = s.search(q, 3, recompute_embeddings=False, **({"skip_search_reorder": True} if name == "d" else {}))
+        out[name] = (res["labels"], res["distances"], list(seen))
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_world2_plugin_searchers_shard_queries(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_plugin_worker, args=(2, port, str(tmp_path), ret), nprocs=2, join=True)
+    q = np.arange(9 * 4, dtype=np.float32).reshape(9, 4)
+    expD = q[:, :1] + np.arange(3, dtype=np.float32)[None]
+    expL = [[str(int(v)) for v in row] for row in (q[:, :1].astype(np.int64) + np.arange(3)[None])]
+    for r in range(2):
+        lo, hi = shard_bounds(9, 2, r)
+        for name in ("h", "d"):
+            labels, D, seen = ret[r][name]
+            assert labels == expL and np.array_equal(D, expD)   # every rank holds the full, ordered result
+            assert seen == [hi - lo]                            # ... having searched only its own slice
