@@ -38,3 +38,25 @@ def load_vamana_golden(golden_dir, metric):
     return dict(prefix=prefix, g=g, coords=coords, pq=pq, codes=codes, max_norm=mx,
                 emb=np.load(golden_dir / "vamana_small_emb.npy"), q=np.load(golden_dir / "vamana_small_queries.npy"),
                 exp=np.load(golden_dir / "vamana_small_expected.npz"))
+
+
+def load_c1(golden_dir, n_queries=40, seed=5):
+    """BASELINE config C1 (the reference's sample document) as a synth.Corpus: 254-token chunks at stride 127, each wrapped in
+    [CLS]=101 / [SEP]=102, plus queries = random 12..30-token spans of the same text (wrapped the same way)."""
+    stream = np.load(golden_dir / "c1_pride_tokens.npz")["tokens"]
+    starts = np.arange(0, max(1, len(stream) - 127), 127)
+    toks, offs = [], [0]
+    for s in starts:
+        body = stream[s:s + 254]
+        toks.append(np.concatenate([[101], body, [102]]).astype(np.uint16))
+        offs.append(offs[-1] + len(toks[-1]))
+    corpus = synth.Corpus(np.concatenate(toks), np.asarray(offs, np.uint64), np.zeros(len(starts), np.int32))
+    rng = np.random.default_rng(seed)
+    qt, qo = [], [0]
+    for _ in range(n_queries):
+        a = int(rng.integers(0, len(stream) - 40))
+        body = stream[a:a + int(rng.integers(12, 31))]
+        qt.append(np.concatenate([[101], body, [102]]).astype(np.uint16))
+        qo.append(qo[-1] + len(qt[-1]))
+    queries = synth.Corpus(np.concatenate(qt), np.asarray(qo, np.uint64), np.zeros(n_queries, np.int32))
+    return corpus, queries

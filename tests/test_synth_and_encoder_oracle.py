@@ -41,3 +41,21 @@ def test_flops_formula_matches_survey():
     assert abs(synth.MINILM_L6.flops_per_chunk(128) / 1e9 - 2.869) < 0.005
     assert abs(synth.MINILM_L6.flops_per_chunk(256) / 1e9 - 6.039) < 0.005
     assert abs(synth.BGE_BASE.flops_per_chunk(128) / 1e9 - 22.35) < 0.02
+
+
+def test_config_c1_fixture(golden_dir):
+    """BASELINE configs[0]: the reference's sample document as a committed token stream (tests/golden/make_c1_fixture.py).
+    With the fp32 BertModel oracle (MiniLM-L6 architecture, synthetic weights) + the torch graph builder + the C HNSW oracle this
+    corpus gives recall@10 = 0.9975 at M=32, ef=64 (calibration run, 36 s of CPU encoding — too slow for this suite; the GPU suite
+    runs the same case end to end in tests/test_gpu_search.py::test_config_c1_pride_and_prejudice)."""
+    from helpers import load_c1
+    z = np.load(golden_dir / "c1_pride_tokens.npz")
+    assert int(z["source_bytes"]) == 772389 and z["tokens"].dtype == np.uint16 and len(z["tokens"]) == 159175
+    assert 1000 <= z["tokens"].min() and z["tokens"].max() < 30000
+    corpus, queries = load_c1(golden_dir)
+    lens = np.diff(corpus.offsets.astype(np.int64))
+    assert corpus.n == 1253 and lens.max() == 256 and lens.min() >= 100 and queries.n == 40
+    assert (corpus.tokens[corpus.offsets[:-1].astype(np.int64)] == 101).all()
+    assert (corpus.tokens[corpus.offsets[1:].astype(np.int64) - 1] == 102).all()
+    # consecutive chunks overlap by half (the reference's 256/128 split)
+    assert np.array_equal(corpus.passage(0)[128:255], corpus.passage(1)[1:128])
