@@ -47,7 +47,7 @@ def test_config_c1_fixture(golden_dir):
     """BASELINE configs[0]: the reference's sample document as a committed token stream (tests/golden/make_c1_fixture.py).
     With the fp32 BertModel oracle (MiniLM-L6 architecture, synthetic weights) + the torch graph builder + the C HNSW oracle this
     corpus gives recall@10 = 0.9975 at M=32, ef=64 (calibration run, 36 s of CPU encoding — too slow for this suite; the GPU suite
-    runs the same case end to end in tests/test_gpu_search.py::test_config_c1_pride_and_prejudice)."""
+    runs the same case end to end in tests/test_gpu_z_config_c1.py)."""
     from helpers import load_c1
     z = np.load(golden_dir / "c1_pride_tokens.npz")
     assert int(z["source_bytes"]) == 772389 and z["tokens"].dtype == np.uint16 and len(z["tokens"]) == 159175
