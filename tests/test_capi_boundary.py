@@ -46,6 +46,13 @@ def test_struct_layouts_match_header(lib):
     p = capi.SearchParams()
     lib.lb2_default_params(ctypes.byref(p))
     assert (p.efSearch, p.beam_size, p.batch_size, p.check_relative_distance, p.recompute) == (64, 1, 0, 1, 1)
+    # DiskANN structs: 8 x int32 + float + uint32 ; int64 + 8 x int32 + float + int32 + int64
+    assert ctypes.sizeof(capi.DiskannParams) == 40 and ctypes.sizeof(capi.DiskannInfo) == 56
+    d = capi.DiskannParams()
+    lib.lb2_diskann_default_params(ctypes.byref(d))
+    assert (d.complexity, d.beam_width, d.deferred_fetch, d.skip_search_reorder, d.recompute_neighbors, d.io_limit) == (64, 1, 1, 0, 0, 0)
+    m = capi.make_diskann_params(48, 3, recompute_embeddings=False, skip_search_reorder=True, prune_ratio=0.25, io_limit=9)
+    assert (m.complexity, m.beam_width, m.deferred_fetch, m.skip_search_reorder, m.io_limit) == (48, 3, 0, 1, 9) and abs(m.prune_ratio - 0.25) < 1e-7
 
 
 def test_weight_count_is_pure_host_arithmetic(lib):
