@@ -1,0 +1,118 @@
+"""Tooling (not the hot path): search-based refinement of a level-0 HNSW adjacency.
+
+The batch builder of graph_build.py needs k-nearest-neighbour candidate lists.  Above a few million points those come from a
+partition-restricted search whose recall is the limit of the final graph (recall@10 0.80 at 10 M).  A graph
+that is merely *navigable* is, however, itself a much better kNN oracle than the partitions it was built from: searching it with
+every point as the query (ef ~ 128) returns lists of far higher recall, and rebuilding level 0 from those lists gives a better
+graph — the same idea as the reference's incremental construction (every insertion is a search over the graph so far,
+faiss/impl/HNSW.cpp:600-894), applied as whole-graph sweeps.  `search_fn` is any batch searcher over the current graph: the CUDA
+stored-vector search (capi.Index.search(..., recompute=False), 6e5 queries/s, i.e. tens of seconds per sweep at 10 M) in
+production, the CPU oracle in the unit test.
+
+Status: validated on CPU at small scale (tests/test_graph_refine.py); not yet wired into bench.py — the large-scale run needs
+GPU time that round 1 no longer had.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+import torch
+
+from .csr import METRIC_INNER_PRODUCT, CSRGraph, csr_from_padded
+from .graph_build import _add_reverse_and_cap, _heuristic_prune
+
+
+def upper_levels(g: CSRGraph, M: int) -> dict[int, tuple[np.ndarray, np.ndarray]]:
+    """{level >= 1: (member ids int64 [n_l], neighbours int32 [n_l, M] padded with -1)} — the shape csr_from_padded takes."""
+    out = {}
+    base = g.node_offsets[:-1].astype(np.int64)
+    for l in range(1, int(g.max_level) + 1):
+        ids = np.nonzero(g.levels > l)[0].astype(np.int64)
+        if ids.size == 0:
+            continue
+        st = g.level_ptr[base[ids] + l].astype(np.int64)
+        en = g.level_ptr[base[ids] + l + 1].astype(np.int64)
+        deg = en - st
+        nb = np.full((ids.size, max(M, int(deg.max()) if deg.size else 0)), -1, np.int32)
+        col = np.arange(nb.shape[1])[None, :]
+        m = col < deg[:, None]
+        nb[m] = g.neighbors[(st[:, None] + col)[m]]
+        out[l] = (ids, nb)
+    return out
+
+
+@torch.no_grad()
+def lists_from_search(search_fn: Callable[[np.ndarray], np.ndarray], x: np.ndarray, k: int, block: int = 65536) -> np.ndarray:
+    """ids [n, k] (−1 padded): for every point the k nearest *other* points the searcher finds.  search_fn(q [b, d]) -> ids
+    [b, >= k + 1] in ascending-distance order (the point itself is usually first and is dropped wherever it appears)."""
+    n = x.shape[0]
+    out = np.full((n, k), -1, np.int64)
+    for b0 in range(0, n, block):
+        b1 = min(n, b0 + block)
+        ids = np.asarray(search_fn(x[b0:b1]), np.int64)
+        me = np.arange(b0, b1)[:, None]
+        keep = (ids != me) & (ids >= 0)
+        rank = np.cumsum(keep, 1) - 1
+        sel = keep & (rank < k)
+        rows = np.nonzero(sel)[0]
+        out[b0 + rows, rank[sel]] = ids[sel]
+    return out
+
+
+@torch.no_grad()
+def rebuild_level0(x, g: CSRGraph, cand: np.ndarray, M: int = 32, alpha: float = 1.0, union_factor: int = 2,
+                   device: str | None = None) -> CSRGraph:
+    """New CSRGraph whose level-0 adjacency is built from `cand` [n, k] (−1 padded) with the batch builder's own steps
+    (neighbour-selection heuristic, reverse edges, re-prune to 2M); levels, upper levels and the entry point are kept."""
+    metric_ip = g.metric_type == METRIC_INNER_PRODUCT
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    xt = xt.to(dev, torch.float32)
+    ci = torch.from_numpy(np.ascontiguousarray(cand)).to(dev)
+    n, k = ci.shape
+    cd = torch.empty((n, k), dtype=torch.float32, device=dev)
+    xs = xt.half() if xt.is_cuda else xt
+    sq = (xt * xt).sum(1)
+    for b0 in range(0, n, 1 << 16):  # exact distances of the candidates, row blocks
+        b1 = min(n, b0 + (1 << 16))
+        cc = ci[b0:b1].clamp(min=0)
+        ip = torch.bmm(xs[cc], xs[b0:b1].unsqueeze(2)).squeeze(2).float()
+        d = -ip if metric_ip else (sq[b0:b1, None] + sq[cc] - 2 * ip)
+        cd[b0:b1] = torch.where(ci[b0:b1] >= 0, d, torch.full_like(d, float("inf")))
+    o = torch.argsort(cd, dim=1, stable=True)
+    ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+    cap = 2 * M
+    fwd = _heuristic_prune(xt, ci, cd, cap, metric_ip, fill=False, alpha=alpha)
+    ui, ud = _add_reverse_and_cap(xt, fwd, union_factor * cap, metric_ip)
+    both = _heuristic_prune(xt, ui, ud, cap, metric_ip, fill=True, alpha=alpha)
+    level0 = both.cpu().numpy().astype(np.int32)
+    return csr_from_padded(g.d, g.metric_type, g.levels, level0, upper_levels(g, M), g.entry_point, M=M)
+
+
+def level0_padded(g: CSRGraph, width: int) -> np.ndarray:
+    """Current level-0 adjacency as int64 [n, width] padded with -1."""
+    base = g.node_offsets[:-1].astype(np.int64)
+    st = g.level_ptr[base].astype(np.int64)
+    deg = g.level_ptr[base + 1].astype(np.int64) - st
+    out = np.full((g.ntotal, max(width, int(deg.max()) if deg.size else 0)), -1, np.int64)
+    col = np.arange(out.shape[1])[None, :]
+    m = col < deg[:, None]
+    out[m] = g.neighbors[(st[:, None] + col)[m]]
+    return out
+
+
+def refine_graph_by_search(x, g: CSRGraph, make_search_fn: Callable[[CSRGraph], Callable[[np.ndarray], np.ndarray]], M: int = 32,
+                           k: int = 48, rounds: int = 1, device: str | None = None) -> CSRGraph:
+    """`rounds` sweeps of: search the current graph with every point -> candidate lists -> rebuild level 0.
+    make_search_fn(graph) returns the batch searcher over that graph (it owns ef and the result width k + 1).  The current
+    adjacency stays in the candidate set: it carries the long links (nearest members of the sparser levels) that pure
+    nearest-neighbour lists lack and that keep the graph navigable."""
+    xn = x.cpu().numpy() if isinstance(x, torch.Tensor) else np.ascontiguousarray(x, np.float32)
+    for _ in range(rounds):
+        found = lists_from_search(make_search_fn(g), xn, k)
+        cand = np.concatenate([found, level0_padded(g, 2 * M)], axis=1)
+        cand.sort(axis=1)                      # group equal ids, then blank the repeats
+        cand[:, 1:][cand[:, 1:] == cand[:, :-1]] = -1
+        g = rebuild_level0(x, g, cand, M=M, device=device)
+    return g
