@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 1024)))
     ap.add_argument("--per-pass", type=int, default=int(os.environ.get("LB2_PER_PASS", 0)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--refine-sweeps", type=int, default=0, help="graph tooling: search-sweep refinement rounds after the batch build (leann_b200/graph_refine.py)")
     ap.add_argument("--diskann", action="store_true", help="extra: the DiskANN/Vamana path over the same corpus (adds ~1-2 min of set-up)")
     return ap.parse_args()
 
@@ -129,6 +130,12 @@ def build_world(args, rank, device):
     t2 = time.time()
     g = build_hnsw_graph(E, M=32, metric="mips", device=f"cuda:{device}")
     log(f"graph: {g.neighbors.size/1e6:.1f} M edges, max_level {g.max_level} ({time.time()-t2:.1f}s)")
+    if args.refine_sweeps > 0:  # opt-in; the default run never takes this branch
+        from leann_b200.graph_refine import gpu_searcher, refine_graph_by_search
+        t3 = time.time()
+        g = refine_graph_by_search(E, g, gpu_searcher(E.data_ptr(), work, device=device), M=32, k=48, rounds=args.refine_sweeps,
+                                   device=f"cuda:{device}")
+        log(f"graph after {args.refine_sweeps} search sweep(s): {g.neighbors.size/1e6:.1f} M edges ({time.time()-t3:.1f}s)")
     index_path = write_leann_index(work, "bench", g, preset, corpus)
     # 3. exact ground truth (brute-force fp32 IP over the same embeddings: run_evaluation.py:358-367 with k=10)
     Qt = torch.from_numpy(Q).to(E.device)

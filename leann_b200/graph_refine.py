@@ -116,3 +116,28 @@ def refine_graph_by_search(x, g: CSRGraph, make_search_fn: Callable[[CSRGraph], 
         cand[:, 1:][cand[:, 1:] == cand[:, :-1]] = -1
         g = rebuild_level0(x, g, cand, M=M, device=device)
     return g
+
+
+def gpu_searcher(vectors_device_ptr: int, workdir, ef: int = 128, k: int = 48, device: int = 0):
+    """make_search_fn for refine_graph_by_search backed by the CUDA stored-vector search: writes the current graph in the
+    reference's CSR format, opens it through the C ABI, attaches the (device-resident) vectors and searches with
+    recompute_embeddings=False.  Untested at the time of writing (round 1 ran out of GPU time); the pieces it calls
+    (write_compact_index, capi.Index, set_vectors_device, search) are the ones bench.py's stored-vector extra uses."""
+    from pathlib import Path
+
+    from . import capi, csr
+
+    def make(g: CSRGraph):
+        f = Path(workdir) / "refine_sweep.index"
+        csr.write_compact_index(str(f), g)
+        idx = capi.Index(str(f), device)
+        idx.set_vectors_device(vectors_device_ptr)
+        params = capi.make_params(ef, 1, 0, True, recompute=False)
+
+        def search(q: np.ndarray) -> np.ndarray:
+            return idx.search(np.ascontiguousarray(q, np.float32), k + 1, params)[1]
+
+        search.close = idx.close  # type: ignore[attr-defined]
+        return search
+
+    return make
