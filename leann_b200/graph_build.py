@@ -64,7 +64,7 @@ def _knn_ivf(x: torch.Tensor, k: int, metric_ip: bool, n_clusters: int | None = 
     n, d = x.shape
     dev = x.device
     C = n_clusters or int(round((n / 10000) ** 0.5 * 32))  # ~1000 clusters at 10 M
-    C = max(8, min(C, n // 64))
+    C = max(1, min(max(8, min(C, n // 64)), n))  # tiny member sets (upper levels when IVF is forced): never more cells than points
     g = torch.Generator(device=dev).manual_seed(seed)
     samp = x[torch.randint(0, n, (min(n, 256 * C),), device=dev, generator=g)]
     cent = samp[torch.randperm(samp.shape[0], device=dev, generator=g)[:C]].clone()

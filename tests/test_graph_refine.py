@@ -46,3 +46,14 @@ def test_one_search_sweep_repairs_a_graph_built_from_poor_candidate_lists(monkey
     l0 = level0_padded(g_ref, 32)
     assert l0.shape[1] == 32 and ((l0 >= 0).sum(1) >= 1).all()
     assert not (l0 == np.arange(n)[:, None]).any()           # no self loops
+
+
+def test_partition_restricted_lists_work_on_tiny_member_sets():
+    """IVF forced on every level (ivf_threshold=0): the upper levels have a handful of members — fewer than the minimum cell count."""
+    import torch
+    x = torch.nn.functional.normalize(torch.randn(3000, 16, generator=torch.Generator().manual_seed(1)), dim=1).numpy()
+    g = gb.build_hnsw_graph(x, M=8, metric="mips", device="cpu", ivf_threshold=0, ivf_refine_rounds=1)
+    assert g.ntotal == 3000 and g.max_level >= 2 and g.neighbors.min() >= 0 and g.neighbors.max() < 3000
+    q = x[:50]
+    _, I, _, _ = Oracle(g, x).search(q, 1, ef=32)
+    assert (I[:, 0] == np.arange(50)).mean() > 0.9   # navigable: a point finds itself
