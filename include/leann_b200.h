@@ -217,6 +217,31 @@ int lb2_diskann_search_device(lb2_index* idx, int64_t nq, const float* d_q, int6
  * order; ids is [nq, cap], n_full [nq].  Valid for calls of at most one wave (4096 queries). */
 int lb2_diskann_last_expansions(lb2_index* idx, int64_t nq, int32_t cap, uint32_t* ids, int32_t* n_full);
 
+/* ------------------------------------------------------------------------------------------------
+ * Graph construction (tooling around the path): the two device stages of a batch-parallel
+ * HNSW build; all pointers are DEVICE pointers, launches go to the default stream, nothing synchronises.
+ *
+ *   lb2_build_insert_search   per point: greedy descent over the upper levels + efConstruction search on level 0
+ *                               HNSW::add_with_locks -> search_neighbors_to_add, faiss/impl/HNSW.cpp:839-894, 609-720
+ *   lb2_build_select          neighbour-selection heuristic over sorted candidates
+ *                               HNSW::shrink_neighbor_list, faiss/impl/HNSW.cpp:426-468
+ * The batch schedule, link merging and the CSR writer are leann_b200/graph_build.py.
+ */
+/* x: [n, d] fp16 (d % 8 == 0); adj0: [n, cap0] level-0 lists, -1 padded (empty rows = not inserted yet);
+ * up_row[n]: first row of a node's level-1 list in up_adj [rows, capU] (level l list = row up_row + l - 1), -1 for
+ * level-0-only nodes; entry / max_level: entry point and its (0-based) level; points[npts]: ids whose vectors are the
+ * queries; out_ids / out_dist: [npts, ef] nearest found, ascending, (-1, FLT_MAX) padded; the point itself is never
+ * returned.  workspace: lb2_build_workspace_bytes(ef, cap0) bytes. */
+int lb2_build_insert_search(const void* d_x_f16, int64_t n, int32_t d, int32_t metric_ip, const int32_t* d_adj0,
+                            int32_t cap0, const int32_t* d_up_row, const int32_t* d_up_adj, int32_t capU, int32_t entry,
+                            int32_t max_level, const int32_t* d_points, int64_t npts, int32_t ef, int32_t* d_out_ids,
+                            float* d_out_dist, void* d_workspace, size_t workspace_bytes);
+size_t lb2_build_workspace_bytes(int32_t ef, int32_t cap0);
+/* pd: [b, K, K] pairwise candidate distances (fp16, or fp32 when pd_is_f32); dn: [b, K] node-to-candidate distances,
+ * ascending; cand: [b, K] ids, -1 padded at the end; out: [b, keep] kept ids / distances, (-1, FLT_MAX) padded. */
+int lb2_build_select(const void* d_pd, int32_t pd_is_f32, const float* d_dn, const int32_t* d_cand, int64_t b, int32_t K,
+                     int32_t keep, int32_t* d_out_ids, float* d_out_dist);
+
 /* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
 int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);

@@ -213,7 +213,10 @@ class _B200SearcherBase(LeannBackendSearcherInterface):
             ids = self._tokenizer(query, truncation=True, max_length=self.preset.max_pos)["input_ids"]
         else:
             ids = query
-        toks = np.asarray(ids, np.uint16).reshape(-1)
+        ids = np.asarray(ids, np.int64).reshape(-1)
+        if ids.size == 0 or ids.min() < 0 or ids.max() >= self.preset.vocab_size or ids.max() > 65535:
+            raise ValueError(f"query token ids must lie in [0, {min(self.preset.vocab_size, 65536)}) and be non-empty")
+        toks = ids.astype(np.uint16)
         emb = self._index.encode_tokens(toks, np.array([0, toks.size], np.uint64))
         return emb.reshape(1, -1)
 
@@ -276,9 +279,10 @@ class B200HnswSearcher(_B200SearcherBase):
             local_prune = True
         elif pruning_strategy == "proportional":
             send_ratio = 1.0
-        if prune_ratio != 0.0 and self._sidecar("pq_pivots.bin").exists() is False:
-            # the reference silently ignores prune_ratio when no PQ files are loaded
-            # (perform_pq_pruning needs hnsw.pq_data_loader, HNSW_search.cpp:442-445)
+        if not self._sidecar("pq_pivots.bin").exists():
+            # the reference ignores prune_ratio AND the strategy flags when no PQ files are loaded
+            # (perform_pq_pruning needs hnsw.pq_data_loader, HNSW_search.cpp:442-445): the same call
+            # succeeds on the stock backend, so it must not raise here
             prune_ratio, local_prune, send_ratio = 0.0, False, 0.0
         params = capi.make_params(complexity, beam_width, batch_size, check_rel, prune_ratio, local_prune, send_ratio,
                                   recompute_embeddings)
@@ -338,8 +342,10 @@ def tokenize_passages(index_path: str, texts, tokenizer, max_len: int) -> None:
     embedding_compute.py:299-305) into the uint16 sidecars the recompute stage reads."""
     toks, offs = [], [0]
     for t in texts:
-        ids = tokenizer(t, truncation=True, max_length=max_len)["input_ids"]
-        toks.append(np.asarray(ids, np.uint16))
+        ids = np.asarray(tokenizer(t, truncation=True, max_length=max_len)["input_ids"], np.int64)
+        if ids.size == 0 or ids.min() < 0 or ids.max() > 65535:
+            raise ValueError("token ids must fit the uint16 passage store (vocabularies up to 65 536 entries) and passages must not be empty")
+        toks.append(ids.astype(np.uint16))
         offs.append(offs[-1] + len(ids))
     p = Path(index_path)
     np.save(p.parent / f"{p.name}.tokens.npy", np.concatenate(toks) if toks else np.zeros(0, np.uint16))

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "lb2_set_option",
     "lb2_diskann_open", "lb2_diskann_info", "lb2_diskann_default_params", "lb2_diskann_search",
     "lb2_diskann_search_device", "lb2_diskann_last_expansions",
+    "lb2_build_insert_search", "lb2_build_workspace_bytes", "lb2_build_select",
     "lb2_test_gemm_f16", "lb2_test_gemm_grouped_f16", "lb2_test_layernorm_f16", "lb2_test_attention_f16",
 ]
 
@@ -122,6 +123,13 @@ def load():
     lib.lb2_test_layernorm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
     lib.lb2_test_attention_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lb2_test_gemm_grouped_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.lb2_build_insert_search.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.lb2_build_workspace_bytes.restype = C.c_size_t
+    lib.lb2_build_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.lb2_build_select.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -301,3 +309,24 @@ class DiskannIndex(Index):
         _check(self._lib.lb2_diskann_last_expansions(self._h, nq, cap, _np_ptr(ids), _np_ptr(n_full)),
                "lb2_diskann_last_expansions")
         return ids, n_full
+
+
+# ---- graph construction stages (device pointers; tooling, see leann_b200/graph_build.py)
+def build_workspace_bytes(ef: int, cap0: int) -> int:
+    return int(load().lb2_build_workspace_bytes(int(ef), int(cap0)))
+
+
+def build_insert_search(d_x_f16: int, n: int, d: int, metric_ip: bool, d_adj0: int, cap0: int, d_up_row: int, d_up_adj: int,
+                        capU: int, entry: int, max_level: int, d_points: int, npts: int, ef: int, d_out_ids: int,
+                        d_out_dist: int, d_workspace: int, workspace_bytes: int) -> None:
+    _check(load().lb2_build_insert_search(C.c_void_p(d_x_f16), int(n), int(d), int(bool(metric_ip)), C.c_void_p(d_adj0),
+                                          int(cap0), C.c_void_p(d_up_row), C.c_void_p(d_up_adj), int(capU), int(entry),
+                                          int(max_level), C.c_void_p(d_points), int(npts), int(ef), C.c_void_p(d_out_ids),
+                                          C.c_void_p(d_out_dist), C.c_void_p(d_workspace), int(workspace_bytes)),
+           "lb2_build_insert_search")
+
+
+def build_select(d_pd: int, pd_is_f32: bool, d_dn: int, d_cand: int, b: int, K: int, keep: int, d_out_ids: int,
+                 d_out_dist: int) -> None:
+    _check(load().lb2_build_select(C.c_void_p(d_pd), int(bool(pd_is_f32)), C.c_void_p(d_dn), C.c_void_p(d_cand), int(b), int(K),
+                                   int(keep), C.c_void_p(d_out_ids), C.c_void_p(d_out_dist)), "lb2_build_select")

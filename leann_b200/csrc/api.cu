@@ -129,6 +129,7 @@ struct lb2_index {
     uint16_t* d_tokens = nullptr;
     uint64_t* d_tok_off = nullptr;
     std::vector<uint64_t> h_tok_off;
+    int max_token = 0;  // largest token id of the attached store (checked against the encoder's vocabulary)
     Encoder enc;
     // tunables
     int cfg_slots = 0;
@@ -262,6 +263,12 @@ bool ensure_state(lb2_index* x, int S, const TravParams& p, bool recompute) {
     x->alloc_p = p;
     x->alloc_recompute = recompute;
     return true;
+}
+
+int max_token(const uint16_t* t, uint64_t n) {
+    uint16_t m = 0;
+    for (uint64_t i = 0; i < n; i++) m = t[i] > m ? t[i] : m;
+    return m;
 }
 
 int next_pow2(int v) {
@@ -695,7 +702,20 @@ void lb2_default_params(lb2_search_params* p) {
     p->pq_pruning_ratio = 0.f; p->local_prune = 0; p->send_neigh_times_ratio = 0.f; p->recompute = 1;
 }
 
+static lb2_index* open_impl(const char* index_path, int device);
+
 lb2_index* lb2_open(const char* index_path, int device) {
+    try {
+        return open_impl(index_path, device);
+    } catch (const std::exception& e) {  // e.g. bad_alloc on a corrupt element count
+        set_error("%s: malformed index (%s)", index_path ? index_path : "(null)", e.what());
+    } catch (...) {
+        set_error("%s: malformed index", index_path ? index_path : "(null)");
+    }
+    return nullptr;
+}
+
+static lb2_index* open_impl(const char* index_path, int device) {
     if (!index_path) { set_error("index_path is null"); return nullptr; }
     // the file is parsed and validated first (host work), so a malformed index is reported as such on any machine
     HostIndex h;
@@ -792,9 +812,17 @@ int lb2_set_passages(lb2_index* x, const uint16_t* tokens, const uint64_t* offse
     if (!use_device(x)) return LB2_ERR_CUDA;
     const int64_t N = x->g.ntotal;
     for (int64_t i = 0; i < N; i++)
-        if (offsets[i + 1] < offsets[i]) { set_error("passage offsets not monotone at %lld", (long long)i); return LB2_ERR_ARG; }
+        if (offsets[i + 1] <= offsets[i]) {  // the reference's tokenizer always emits [CLS] .. [SEP]: no empty passages
+            set_error("passage %lld is empty or its offsets are not monotone", (long long)i);
+            return LB2_ERR_ARG;
+        }
     const uint64_t total = offsets[N] - offsets[0];
     if (offsets[0] != 0) { set_error("passage offsets must start at 0"); return LB2_ERR_ARG; }
+    const int max_tok = max_token(tokens, total);
+    if (x->enc.loaded && max_tok >= x->enc.cfg.vocab_size) {
+        set_error("passage store holds token id %d but the encoder's vocabulary has %d entries", max_tok, x->enc.cfg.vocab_size);
+        return LB2_ERR_ARG;
+    }
     if (!dev_alloc(&x->d_tokens, (size_t)total + 8) || !dev_alloc(&x->d_tok_off, (size_t)N + 1)) return LB2_ERR_CUDA;
     if (cudaMemcpy(x->d_tokens, tokens, total * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(x->d_tok_off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -802,6 +830,7 @@ int lb2_set_passages(lb2_index* x, const uint16_t* tokens, const uint64_t* offse
         return LB2_ERR_CUDA;
     }
     x->h_tok_off.assign(offsets, offsets + N + 1);
+    x->max_token = max_tok;
     return LB2_OK;
 }
 
@@ -815,6 +844,10 @@ int lb2_set_encoder(lb2_index* x, const lb2_encoder_config* c, const float* w, s
     if (!x || !c || !w) { set_error("null argument"); return LB2_ERR_ARG; }
     if (!use_device(x)) return LB2_ERR_CUDA;
     EncoderConfig e{c->vocab_size, c->hidden, c->layers, c->heads, c->ffn, c->max_pos, c->type_vocab, c->ln_eps, c->pooling, c->normalize};
+    if (x->d_tokens && x->max_token >= c->vocab_size) {  // the embedding kernel indexes word_emb unchecked
+        set_error("attached passages hold token id %d but the encoder's vocabulary has %d entries", x->max_token, c->vocab_size);
+        return LB2_ERR_ARG;
+    }
     if (!encoder_load(&x->enc, e, w, n)) return LB2_ERR_ARG;
     x->enc.num_sms = x->num_sms;
     return LB2_OK;
@@ -910,6 +943,13 @@ int lb2_encode_tokens(lb2_index* x, int64_t n, const uint16_t* tokens, const uin
     if (!x || (n > 0 && (!tokens || !offsets || !out))) { set_error("null argument"); return LB2_ERR_ARG; }
     if (!use_device(x)) return LB2_ERR_CUDA;
     if (n == 0) return LB2_OK;
+    if (offsets[0] != 0) { set_error("offsets must start at 0"); return LB2_ERR_ARG; }
+    for (int64_t i = 0; i < n; i++)
+        if (offsets[i + 1] <= offsets[i]) { set_error("sequence %lld is empty or its offsets are not monotone", (long long)i); return LB2_ERR_ARG; }
+    if (x->enc.loaded && max_token(tokens, offsets[n]) >= x->enc.cfg.vocab_size) {
+        set_error("token id out of range for a vocabulary of %d entries", x->enc.cfg.vocab_size);
+        return LB2_ERR_ARG;
+    }
     uint16_t* dt = nullptr;
     uint64_t* doff = nullptr;
     const uint64_t total = offsets[n];
@@ -927,7 +967,20 @@ void lb2_diskann_default_params(lb2_diskann_params* p) {
     p->complexity = 64; p->beam_width = 1; p->deferred_fetch = 1; p->global_pruning = 1;
 }
 
+static lb2_index* diskann_open_impl(const char* index_prefix, const char* partition_prefix, int metric, int device);
+
 lb2_index* lb2_diskann_open(const char* index_prefix, const char* partition_prefix, int metric, int device) {
+    try {
+        return diskann_open_impl(index_prefix, partition_prefix, metric, device);
+    } catch (const std::exception& e) {
+        set_error("%s: malformed index (%s)", index_prefix ? index_prefix : "(null)", e.what());
+    } catch (...) {
+        set_error("%s: malformed index", index_prefix ? index_prefix : "(null)");
+    }
+    return nullptr;
+}
+
+static lb2_index* diskann_open_impl(const char* index_prefix, const char* partition_prefix, int metric, int device) {
     if (!index_prefix) { set_error("index_prefix is null"); return nullptr; }
     VamanaHost h;
     std::string err;

@@ -342,11 +342,13 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
                                const CUtensorMap& tr, const float* bias, int M, int N, int K, int c_group, int num_sms) {
     using L = GemmSmem<GEMM_BLOCK_N, GEMM_STAGES>;
     auto kern = gemm_f16_tn_kernel<GEMM_BLOCK_N, GEMM_STAGES, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static thread_local int attr_dev_mask[8] = {0};  // the opt-in is per device: remember which devices have it
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 256 || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;

@@ -42,6 +42,17 @@ struct Reader {
             *err = "vector length " + std::to_string(n) + " exceeds sanity bound " + std::to_string(max_count);
             return ok = false;
         }
+        {   // a count larger than what is left of the file is a corrupt header, not an allocation request
+            const long here = ftell(f);
+            if (here >= 0 && fseek(f, 0, SEEK_END) == 0) {
+                const long end = ftell(f);
+                fseek(f, here, SEEK_SET);
+                if (end >= here && n * sizeof(T) > static_cast<uint64_t>(end - here)) {
+                    *err = "unexpected end of file: a vector of " + std::to_string(n) + " elements does not fit in what is left";
+                    return ok = false;
+                }
+            }
+        }
         v->resize(n);
         return raw(v->data(), n * sizeof(T));
     }

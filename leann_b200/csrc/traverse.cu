@@ -502,11 +502,8 @@ bool launch_step(cudaStream_t s, const DevGraph& g, const TravParams& p, const T
         set_error("search parameters need %zu bytes of shared memory per CTA (efSearch/beam too large)", smem);
         return false;
     }
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
+    if (smem > 48 * 1024)  // per device, so not cached in a process-wide static (a handle may live on any GPU)
         LB2_CUDA_OK(cudaFuncSetAttribute(hnsw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     const int grid = (st.S + STEP_WARPS - 1) / STEP_WARPS;
     hnsw_step_kernel<<<grid, STEP_WARPS * 32, smem, s>>>(g, p, st, max_iters);
     LB2_CUDA_OK(cudaGetLastError());

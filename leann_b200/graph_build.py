@@ -238,6 +238,54 @@ def _add_reverse_and_cap(x: torch.Tensor, nbr: torch.Tensor, cap: int, metric_ip
 
 
 @torch.no_grad()
+def _build_level_exact(x, levels, members, l, cap, metric_ip, knn_factor=1.5, n_scales=2, alpha=1.0, union_factor=2,
+                       ivf_threshold=2_500_000, ivf_refine_rounds=6) -> np.ndarray:
+    """One level of the batch builder: links among `members` (global ids, all with levels > l).  Returns global
+    neighbour ids int32 [len(members), cap], -1 padded."""
+    dev = x.device
+    if len(members) <= 1:
+        return np.full((len(members), cap), -1, np.int32)
+    mt = torch.from_numpy(members).to(dev)
+    xm = x[mt]
+    nm = len(members)
+    # multi-scale candidates: nearest members, plus nearest among the (sparser) members of
+    # the next levels up.  The sparse samples play the role of HNSW's early insertions and
+    # supply the long links a pure kNN graph lacks.
+    if nm > ivf_threshold:  # brute force is O(n^2): partition-restricted search beyond a few million points
+        ci, cd = _knn_ivf(xm, int(cap * knn_factor), metric_ip)
+        ci, cd = _refine_knn(xm, ci, cd, metric_ip, rounds=ivf_refine_rounds)
+    else:
+        ci, cd = _knn(xm, xm, int(cap * knn_factor), metric_ip, torch.arange(nm, device=dev))
+    cis, cds = [ci], [cd]
+    for s_up in range(1, n_scales + 1):
+        sub = np.nonzero(levels[members] > l + s_up)[0]
+        if len(sub) < 2:
+            break
+        st = torch.from_numpy(sub).to(dev)
+        pos = torch.full((nm,), -1, dtype=torch.int64, device=dev)
+        pos[st] = torch.arange(len(sub), device=dev)
+        di, dv = _knn(xm, xm[st], max(2, cap // 2), metric_ip, pos)
+        cis.append(st[di])
+        cds.append(dv)
+    ci, cd = torch.cat(cis, 1), torch.cat(cds, 1)
+    o = torch.argsort(cd, dim=1, stable=True)
+    ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+    o = torch.argsort(ci, dim=1, stable=True)  # group equal ids (distance order kept inside a group)
+    ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+    dup = torch.zeros_like(ci, dtype=torch.bool)
+    dup[:, 1:] = ci[:, 1:] == ci[:, :-1]
+    ci = torch.where(dup, torch.full_like(ci, -1), ci)
+    cd = torch.where(dup, torch.full_like(cd, float("inf")), cd)
+    o = torch.argsort(cd, dim=1, stable=True)
+    ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+    fwd = _heuristic_prune(xm, ci, cd, cap, metric_ip, fill=False, alpha=alpha)
+    ui, ud = _add_reverse_and_cap(xm, fwd, union_factor * cap, metric_ip)
+    both = _heuristic_prune(xm, ui, ud, cap, metric_ip, fill=True, alpha=alpha)
+    gl = torch.where(both >= 0, mt[both.clamp(min=0)], torch.full_like(both, -1))
+    return gl.cpu().numpy().astype(np.int32)
+
+
+@torch.no_grad()
 def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
                      knn_factor: float = 1.5, n_scales: int = 2, alpha: float = 1.0, union_factor: int = 2,
                      ivf_threshold: int = 2_500_000, ivf_refine_rounds: int = 6, verbose: bool = False) -> CSRGraph:
@@ -253,47 +301,8 @@ def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, 
     for l in range(max_level, -1, -1):
         members = np.nonzero(levels > l)[0]
         cap = 2 * M if l == 0 else M
-        if len(members) <= 1:
-            nb = np.full((len(members), cap), -1, np.int32)
-        else:
-            mt = torch.from_numpy(members).to(dev)
-            xm = x[mt]
-            nm = len(members)
-            # multi-scale candidates: nearest members, plus nearest among the (sparser) members of
-            # the next levels up.  The sparse samples play the role of HNSW's early insertions and
-            # supply the long links a pure kNN graph lacks.
-            if nm > ivf_threshold:  # brute force is O(n^2): partition-restricted search beyond a few million points
-                ci, cd = _knn_ivf(xm, int(cap * knn_factor), metric_ip)
-                ci, cd = _refine_knn(xm, ci, cd, metric_ip, rounds=ivf_refine_rounds)
-            else:
-                ci, cd = _knn(xm, xm, int(cap * knn_factor), metric_ip, torch.arange(nm, device=dev))
-            cis, cds = [ci], [cd]
-            for s_up in range(1, n_scales + 1):
-                sub = np.nonzero(levels[members] > l + s_up)[0]
-                if len(sub) < 2:
-                    break
-                st = torch.from_numpy(sub).to(dev)
-                pos = torch.full((nm,), -1, dtype=torch.int64, device=dev)
-                pos[st] = torch.arange(len(sub), device=dev)
-                di, dv = _knn(xm, xm[st], max(2, cap // 2), metric_ip, pos)
-                cis.append(st[di])
-                cds.append(dv)
-            ci, cd = torch.cat(cis, 1), torch.cat(cds, 1)
-            o = torch.argsort(cd, dim=1, stable=True)
-            ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
-            o = torch.argsort(ci, dim=1, stable=True)  # group equal ids (distance order kept inside a group)
-            ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
-            dup = torch.zeros_like(ci, dtype=torch.bool)
-            dup[:, 1:] = ci[:, 1:] == ci[:, :-1]
-            ci = torch.where(dup, torch.full_like(ci, -1), ci)
-            cd = torch.where(dup, torch.full_like(cd, float("inf")), cd)
-            o = torch.argsort(cd, dim=1, stable=True)
-            ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
-            fwd = _heuristic_prune(xm, ci, cd, cap, metric_ip, fill=False, alpha=alpha)
-            ui, ud = _add_reverse_and_cap(xm, fwd, union_factor * cap, metric_ip)
-            both = _heuristic_prune(xm, ui, ud, cap, metric_ip, fill=True, alpha=alpha)
-            gl = torch.where(both >= 0, mt[both.clamp(min=0)], torch.full_like(both, -1))
-            nb = gl.cpu().numpy().astype(np.int32)
+        nb = _build_level_exact(x, levels, members, l, cap, metric_ip, knn_factor, n_scales, alpha, union_factor,
+                                ivf_threshold, ivf_refine_rounds)
         if l == 0:
             level0 = nb
         else:
@@ -301,4 +310,200 @@ def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, 
         if verbose:
             print(f"  level {l}: {len(members)} nodes, mean degree {(nb >= 0).sum(1).mean():.1f}")
     entry = int(np.nonzero(levels == levels.max())[0][0])
+    return csr_from_padded(d, METRIC_INNER_PRODUCT if metric_ip else METRIC_L2, levels, level0, upper, entry, M=M)
+
+
+# ------------------------------------------------------------------------------------------------
+# Incremental (insertion-as-search) builder: the reference's construction, batch-parallel on the GPU.
+# Device stages: csrc/graph_build.cu (lb2_build_insert_search, lb2_build_select); this file owns the
+# batch schedule and the link bookkeeping (torch tensors as device buffers).
+
+@torch.no_grad()
+def _select_rows(xs: torch.Tensor, me: torch.Tensor, cand: torch.Tensor, cd: torch.Tensor, keep: int, metric_ip: bool,
+                 sq: torch.Tensor | None, block: int = 4096):
+    """Neighbour-selection heuristic (HNSW::shrink_neighbor_list, faiss/impl/HNSW.cpp:426-468) over candidate rows
+    sorted by distance (cand int32 [b, K] -1 padded at the end, cd fp32 [b, K]).  Pairwise candidate distances come from
+    one batched GEMM per row block; the sequential keep/drop scan is lb2_build_select (one warp per row).
+    Returns (ids int32 [b, keep] -1 padded, dist fp32 [b, keep])."""
+    from . import capi
+
+    b, K = cand.shape
+    out_i = torch.empty((b, keep), dtype=torch.int32, device=cand.device)
+    out_d = torch.empty((b, keep), dtype=torch.float32, device=cand.device)
+    for b0 in range(0, b, block):
+        b1 = min(b, b0 + block)
+        c = cand[b0:b1].clamp(min=0).long()
+        cv = xs[c]                                             # [r, K, d] fp16
+        pd = torch.bmm(cv, cv.transpose(1, 2))                 # [r, K, K] fp16 inner products
+        if metric_ip:
+            pd = -pd
+        else:
+            s = sq[c]
+            pd = (s[:, :, None] + s[:, None, :]).half() - 2 * pd
+        pd = pd.contiguous()
+        ci = cand[b0:b1].contiguous()
+        di = cd[b0:b1].contiguous()
+        capi.build_select(pd.data_ptr(), False, di.data_ptr(), ci.data_ptr(), b1 - b0, K, keep,
+                          out_i[b0:b1].data_ptr(), out_d[b0:b1].data_ptr())
+        del cv, pd
+    return out_i, out_d
+
+
+@torch.no_grad()
+def _merge_incoming(xs, sq, adj, adjd, dst, src, dd, cap: int, metric_ip: bool, r_in: int = 32):
+    """Reverse links of a batch (add_link, faiss/impl/HNSW.cpp:510-552, applied per target instead of per edge): the
+    incoming edges (dst <- src at distance dd) are appended to dst's list while there is room; a list that would
+    overflow is re-selected with the heuristic over (current list + its r_in nearest incoming)."""
+    if dst.numel() == 0:
+        return
+    dev = adj.device
+    o = torch.argsort(dd, stable=True)
+    dst, src, dd = dst[o], src[o], dd[o]
+    o = torch.argsort(dst, stable=True)
+    dst, src, dd = dst[o], src[o], dd[o]
+    uniq, inv, counts = torch.unique_consecutive(dst, return_inverse=True, return_counts=True)
+    starts = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(dst.numel(), device=dev) - starts[inv]
+    m = rank < r_in
+    u = uniq.numel()
+    inc_i = torch.full((u, r_in), -1, dtype=torch.int32, device=dev)
+    inc_d = torch.full((u, r_in), float("inf"), dtype=torch.float32, device=dev)
+    inc_i[inv[m], rank[m]] = src[m].int()
+    inc_d[inv[m], rank[m]] = dd[m]
+    ex_i, ex_d = adj[uniq], adjd[uniq]
+    mi = torch.cat([ex_i, inc_i], 1)
+    md = torch.cat([ex_d, inc_d], 1)
+    md = torch.where(mi >= 0, md, torch.full_like(md, float("inf")))
+    o = torch.argsort(md, dim=1, stable=True)
+    mi, md = torch.gather(mi, 1, o), torch.gather(md, 1, o)
+    total = (mi >= 0).sum(1)
+    over = total > cap
+    new_i, new_d = mi[:, :cap].clone(), md[:, :cap].clone()
+    if bool(over.any()):
+        rows = torch.nonzero(over)[:, 0]
+        si, sd = _select_rows(xs, uniq[rows], mi[rows], md[rows], cap, metric_ip, sq)
+        new_i[rows], new_d[rows] = si, sd
+    adj[uniq] = new_i
+    adjd[uniq] = new_d
+
+
+def upper_level_arrays(levels: np.ndarray, upper: dict, M: int, dev):
+    """The upper levels in lb2_build_insert_search's layout: up_row int32 [n] = first row of a node's level-1 list in
+    up_adj int32 [rows, M] (level l = row up_row + l - 1), -1 for nodes that live on level 0 only."""
+    n_up = np.maximum(np.asarray(levels).astype(np.int64) - 1, 0)
+    up_row_h = np.where(n_up > 0, np.cumsum(n_up) - n_up, -1).astype(np.int32)
+    up_adj = torch.full((max(1, int(n_up.sum())), M), -1, dtype=torch.int32, device=dev)
+    for l, (ids, nb) in upper.items():
+        rows = torch.from_numpy(up_row_h[ids].astype(np.int64) + l - 1).to(dev)
+        up_adj[rows] = torch.from_numpy(np.ascontiguousarray(nb[:, :M], np.int32)).to(dev)
+    return torch.from_numpy(up_row_h).to(dev), up_adj
+
+
+@torch.no_grad()
+def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
+                                 ef_construction: int = 200, growth: float = 0.25, min_seed: int = 20000,
+                                 max_batch: int = 1 << 20, sweeps: int = 0, verbose: bool = False) -> CSRGraph:
+    """HNSW construction the way the reference does it — every point is inserted by searching the graph built so far
+    (hnsw_add_vertices, faiss/IndexHNSW.cpp:59-280: upper levels first, level-0-only points last) — run batch-parallel
+    on the GPU: the points of a batch search concurrently (lb2_build_insert_search, one warp per point), select their
+    links with the heuristic (lb2_build_select) and their reverse links are merged per target.  A batch never exceeds
+    `growth` x the points already inserted, so a new point misses at most that share of its potential neighbours at
+    insertion time; later insertions link back to it, and `sweeps` optional passes re-search every point on the finished
+    graph to repair what the batches missed.  The upper levels (3 % of the points) and the level-0 seed among them are
+    built exactly (brute-force lists) by the batch builder above.  CUDA only."""
+    from . import capi
+
+    metric_ip = metric.lower() in ("mips", "cosine", "ip")
+    dev = torch.device(device or "cuda")
+    if dev.type != "cuda":
+        raise RuntimeError("build_hnsw_graph_incremental needs a CUDA device (csrc/graph_build.cu); use build_hnsw_graph on CPU")
+    x = emb if isinstance(emb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(emb, np.float32))
+    x = x.to(dev, torch.float32)
+    n, d = x.shape
+    if d % 8:
+        raise ValueError("dimension must be a multiple of 8")
+    cap0 = 2 * M
+    levels = draw_levels(n, M, seed)
+    max_level = int(levels.max()) - 1
+    upper = {}
+    for l in range(max_level, 0, -1):
+        members = np.nonzero(levels > l)[0]
+        upper[l] = (members.astype(np.int64), _build_level_exact(x, levels, members, l, M, metric_ip))
+    entry = int(np.nonzero(levels == levels.max())[0][0])
+    # seed of level 0: every node that also lives above, topped up with the first level-0-only points
+    is_seed = levels > 1
+    short = min(n, min_seed) - int(is_seed.sum())
+    if short > 0:
+        is_seed[np.nonzero(~is_seed)[0][:short]] = True
+    seed_ids = np.nonzero(is_seed)[0]
+    rest = np.nonzero(~is_seed)[0]
+    seed_nb = _build_level_exact(x, levels, seed_ids, 0, cap0, metric_ip)
+    xs = x.half().contiguous()
+    sq = None if metric_ip else (x * x).sum(1)
+    adj = torch.full((n, cap0), -1, dtype=torch.int32, device=dev)
+    adjd = torch.full((n, cap0), float("inf"), dtype=torch.float32, device=dev)
+    st = torch.from_numpy(seed_ids).to(dev)
+    snb = torch.from_numpy(seed_nb).to(dev)
+    adj[st] = snb
+    for b0 in range(0, len(seed_ids), 1 << 16):  # distances of the seed links
+        rows = st[b0:b0 + (1 << 16)]
+        c = snb[b0:b0 + (1 << 16)].clamp(min=0).long()
+        ip = torch.bmm(xs[c], xs[rows].unsqueeze(2)).squeeze(2).float()
+        dd = -ip if metric_ip else (sq[rows][:, None] + sq[c] - 2 * ip)
+        adjd[rows] = torch.where(snb[b0:b0 + (1 << 16)] >= 0, dd, torch.full_like(dd, float("inf")))
+    up_row, up_adj = upper_level_arrays(levels, upper, M, dev)
+    ws_bytes = capi.build_workspace_bytes(ef_construction, cap0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def search(points: torch.Tensor):
+        b = points.numel()
+        oi = torch.empty((b, ef_construction), dtype=torch.int32, device=dev)
+        od = torch.empty((b, ef_construction), dtype=torch.float32, device=dev)
+        capi.build_insert_search(xs.data_ptr(), n, d, metric_ip, adj.data_ptr(), cap0, up_row.data_ptr(), up_adj.data_ptr(), M,
+                                 entry, max_level, points.data_ptr(), b, ef_construction, oi.data_ptr(), od.data_ptr(),
+                                 ws.data_ptr(), ws_bytes)
+        return oi, od
+
+    n_in = len(seed_ids)
+    pos = 0
+    rest_t = torch.from_numpy(rest.astype(np.int32)).to(dev)
+    while pos < len(rest):
+        b = int(min(max(1024, growth * n_in), max_batch, len(rest) - pos))
+        pts = rest_t[pos:pos + b].contiguous()
+        ci, cd = search(pts)
+        fi, fd = _select_rows(xs, pts, ci, cd, cap0, metric_ip, sq)
+        p64 = pts.long()
+        adj[p64] = fi
+        adjd[p64] = fd
+        v = fi >= 0
+        src = p64[:, None].expand_as(fi)[v]
+        _merge_incoming(xs, sq, adj, adjd, fi[v].long(), src, fd[v], cap0, metric_ip)
+        pos += b
+        n_in += b
+        if verbose:
+            print(f"  inserted {n_in}/{n} (batch {b}), mean degree {(adj[p64] >= 0).sum(1).float().mean().item():.1f}", flush=True)
+    for _ in range(sweeps):  # repair pass: re-search every point on the finished graph, merge into its list
+        for b0 in range(0, n, max_batch):
+            pts = torch.arange(b0, min(n, b0 + max_batch), dtype=torch.int32, device=dev)
+            ci, cd = search(pts)
+            p64 = pts.long()
+            mi = torch.cat([adj[p64], ci], 1)
+            md = torch.cat([adjd[p64], cd], 1)
+            o = torch.argsort(mi, dim=1, stable=True)          # blank repeated ids
+            mi, md = torch.gather(mi, 1, o), torch.gather(md, 1, o)
+            dup = torch.zeros_like(mi, dtype=torch.bool)
+            dup[:, 1:] = mi[:, 1:] == mi[:, :-1]
+            md = torch.where(dup | (mi < 0), torch.full_like(md, float("inf")), md)
+            mi = torch.where(dup, torch.full_like(mi, -1), mi)
+            o = torch.argsort(md, dim=1, stable=True)
+            mi, md = torch.gather(mi, 1, o), torch.gather(md, 1, o)
+            old = adj[p64].clone()
+            fi, fd = _select_rows(xs, pts, mi.contiguous(), md.contiguous(), cap0, metric_ip, sq)
+            adj[p64] = fi
+            adjd[p64] = fd
+            # reverse links for edges that are new
+            isnew = (fi[:, :, None] != old[:, None, :]).all(2) & (fi >= 0)
+            src = p64[:, None].expand_as(fi)[isnew]
+            _merge_incoming(xs, sq, adj, adjd, fi[isnew].long(), src, fd[isnew], cap0, metric_ip)
+    level0 = adj.cpu().numpy()
     return csr_from_padded(d, METRIC_INNER_PRODUCT if metric_ip else METRIC_L2, levels, level0, upper, entry, M=M)

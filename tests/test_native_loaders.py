@@ -32,6 +32,14 @@ def test_hnsw_loader_rejects_malformed_files(lib, golden_dir, tmp_path):
     gpu_or_none(open_err(lib.lb2_open, str(f).encode(), 0))
     f.write_bytes(good[: len(good) // 2])
     assert "end of file" in open_err(lib.lb2_open, str(f).encode(), 0)
+    # a corrupt element count must come back as an error string, never as bad_alloc across the C boundary
+    import struct
+    from leann_b200.csr import read_compact_index
+    nnz = read_compact_index(str(golden_dir / "hnsw_small_ip.index")).neighbors.size
+    pos = good.rfind(struct.pack("<Q", nnz))  # header of the last vec<> (compact_neighbors_data), the loosely bounded one
+    assert pos > 0
+    f.write_bytes(good[:pos] + struct.pack("<Q", (1 << 39) + 7) + good[pos + 8:])
+    assert "end of file" in open_err(lib.lb2_open, str(f).encode(), 0)
     f.write_bytes(b"XXXX" + good[4:])
     msg = open_err(lib.lb2_open, str(f).encode(), 0)
     assert msg and "no CUDA device" not in msg
