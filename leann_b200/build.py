@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libleann_b200.so"
-SOURCES = ["api.cu", "traverse.cu", "encoder.cu", "gemm_tcgen05.cu", "index_io.cpp", "vamana.cu", "vamana_io.cpp", "graph_build.cu"]
+SOURCES = ["api.cu", "traverse.cu", "encoder.cu", "gemm_tcgen05.cu", "index_io.cpp", "vamana.cu", "vamana_io.cpp", "graph_build.cu", "attention_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -1,0 +1,280 @@
+// Recompute stage, self-attention on the 5th-generation tensor cores (head_dim 32, sequences <= 256 tokens:
+// all-MiniLM-L6-v2).  softmax(Q K^T / sqrt(hd)) V per (passage, head), no padding keys — the arithmetic of
+// BertSelfAttention inside SentenceTransformer.encode (leann-core/src/leann/embedding_compute.py:161, 231-239).
+//
+// One work item = (passage s, block of 128 query rows, head h).  Persistent CTAs, two per SM (256 TMEM columns
+// each), 192 threads:
+//   warp 4 lane 0 : TMA producer.  The head-major QKV activation [heads][tokens][q(32) | k(32) | v(32)] is read
+//                   through two 3-D tensor maps: rows of (q | k) = 128 B into a SWIZZLE_128B tile (one load serves
+//                   both MMA operands of S), rows of v = 64 B into a SWIZZLE_64B tile; 64-row boxes, 2-stage ring.
+//   warp 5 lane 0 : MMA issuer.   S[128, Lp] = Q . K^T : two tcgen05.mma (K = 16 each), A = the query rows of the
+//                   (q | k) tile, B = its key half (descriptor start + 64 B), both K-major SW128; N = Lp = L
+//                   rounded up to 16 (<= 256).  Then O[128, 32] = P . V : Lp / 16 tcgen05.mma with A = P read from
+//                   TENSOR MEMORY and B = the v tile as an MN-major operand (rows = keys, no transpose needed).
+//   warps 0..3    : softmax, one thread per query row (tcgen05.ld 32x32b: TMEM lane = row, no shuffles): pass 1
+//                   row maximum, pass 2 p = 2^((s - m) * scale * log2 e), row sum, fp16 P written back to TMEM
+//                   IN PLACE over the columns of S already consumed (tcgen05.st), zeros for keys >= L.  After the
+//                   P.V MMAs: O from TMEM -> * 1/sum -> fp16 -> ctx[token][h * 32 ..] (64 B per row).
+// TMEM columns of a CTA: S = [0, Lp) fp32, P = [0, Lp / 2) packed fp16 (aliases S), O = [128, 160) (aliases dead S
+// columns; the first P.V MMA overwrites).  Barriers: full/empty (smem ring), s_ready, p_ready, o_ready, t_free.
+// Bound: the softmax (MUFU ex2 + issue slots), not the tensor pipe — 4.L.h flops per token are 5 % of the layer.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace lb2 {
+
+namespace {
+
+constexpr int ATC_HD = 32;
+constexpr int ATC_TM = 128;    // query rows per item
+constexpr int ATC_MAXL = 256;  // keys per passage (TMEM columns of S)
+constexpr int ATC_BOX = 64;    // rows per TMA box
+constexpr int ATC_THREADS = 192;
+constexpr int ATC_QK_BYTES = ATC_MAXL * 128;
+constexpr int ATC_V_BYTES = ATC_MAXL * 64;
+constexpr int ATC_STAGE_BYTES = ATC_QK_BYTES + ATC_V_BYTES;
+constexpr int ATC_STAGES = 2;
+constexpr int ATC_BAR_OFFSET = ATC_STAGES * ATC_STAGE_BYTES;
+constexpr int ATC_SMEM = ATC_BAR_OFFSET + 16 * 8 + 16 + 1024;
+constexpr int ATC_TMEM_COLS = 256;
+constexpr int ATC_O_COL = 128;
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// work list: one entry per (passage, 128-row query block); a passage's blocks are adjacent
+__global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_len, int n_seq, int* __restrict__ items,
+                                          int* __restrict__ count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seq) return;
+    const int nb = (seq_len[s] + ATC_TM - 1) / ATC_TM;
+    const int base = atomicAdd(count, nb);
+    for (int i = 0; i < nb; i++) items[base + i] = s * 8 + i;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
+                    const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
+                    const int* __restrict__ items, const int* __restrict__ n_items, int row_base, int heads, int hidden,
+                    __half* __restrict__ ctx) {
+    extern __shared__ uint8_t att_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ATC_BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + ATC_STAGES;
+    uint64_t* s_ready = empty_bar + ATC_STAGES;
+    uint64_t* p_ready = s_ready + 1;
+    uint64_t* o_ready = p_ready + 1;
+    uint64_t* t_free = o_ready + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = *n_items * heads;
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_qk);
+        ptx::prefetch_tmap(&tmap_v);
+        for (int i = 0; i < ATC_STAGES; i++) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        ptx::mbar_init(s_ready, 1);
+        ptx::mbar_init(p_ready, 4);
+        ptx::mbar_init(o_ready, 1);
+        ptx::mbar_init(t_free, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 5) {
+        ptx::tmem_alloc(tmem_ptr, ATC_TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ===== TMA producer
+            int it = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
+                const int stage = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                const int item = items[w / heads], h = w % heads;
+                const int s = item >> 3;
+                const int L = seq_len[s];
+                const int row0 = seq_start[s] - row_base;
+                const int nbox = (L + ATC_BOX - 1) / ATC_BOX;
+                ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                uint8_t* qk = smem + stage * ATC_STAGE_BYTES;
+                uint8_t* v = qk + ATC_QK_BYTES;
+                ptx::mbar_expect_tx(&full_bar[stage], nbox * ATC_BOX * (128 + 64));
+                for (int b = 0; b < nbox; b++) {
+                    ptx::tma_load_3d(qk + b * ATC_BOX * 128, &tmap_qk, &full_bar[stage], 0, row0 + b * ATC_BOX, h);
+                    ptx::tma_load_3d(v + b * ATC_BOX * 64, &tmap_v, &full_bar[stage], 2 * ATC_HD, row0 + b * ATC_BOX, h);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // ===== MMA issuer
+            int it = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
+                const int stage = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                const int item = items[w / heads];
+                const int s = item >> 3, qb = item & 7;
+                const int L = seq_len[s];
+                const int Lp = (L + 15) & ~15;
+                ptx::mbar_wait(&full_bar[stage], ph);
+                ptx::mbar_wait(t_free, (it & 1) ^ 1);  // the previous item's O has been read out of TMEM
+                ptx::tc_fence_after();
+                const uint32_t qk = ptx::smem_u32(smem + stage * ATC_STAGE_BYTES);
+                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + qb * ATC_TM * 128);
+                const uint64_t b_desc = ptx::make_sw128_kmajor_desc(qk) + 4;  // the k half of the (q | k) rows: +64 B
+                const uint32_t idesc_s = ptx::make_idesc_f16(ATC_TM, Lp);
+#pragma unroll
+                for (int k = 0; k < ATC_HD / 16; k++) ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0);
+                ptx::umma_commit(s_ready);
+                ptx::mbar_wait(p_ready, it & 1);
+                ptx::tc_fence_after();
+                const uint32_t vb = qk + ATC_QK_BYTES;
+                const uint32_t idesc_o = ptx::make_idesc_f16(ATC_TM, ATC_HD) | ptx::IDESC_B_MN_MAJOR;
+                for (int j = 0; j < Lp / 16; j++)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (1 KB) of V
+                    ptx::umma_f16_ts(tmem_base + ATC_O_COL, tmem_base + 8 * j, ptx::make_mn_major_desc(vb + j * 1024, 64), idesc_o,
+                                     j != 0);
+                ptx::umma_commit(o_ready);
+                ptx::umma_commit(&empty_bar[stage]);
+            }
+        }
+    } else {
+        // ===== softmax + output: thread = query row
+        const float scale_log2 = rsqrtf(static_cast<float>(ATC_HD)) * 1.4426950408889634f;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        int it = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
+            const int item = items[w / heads], h = w % heads;
+            const int s = item >> 3, qb = item & 7;
+            const int L = seq_len[s];
+            const int q = qb * ATC_TM + threadIdx.x;
+            const int nch = (L + 31) >> 5;
+            ptx::mbar_wait(s_ready, it & 1);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            // pass 1: row maximum over the L valid keys
+            float m = -INFINITY;
+            for (int c = 0; c < nch; c++) {
+                ptx::tmem_ld_32x32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+                if (c * 32 + 32 <= L) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) m = (c * 32 + j < L) ? fmaxf(m, __uint_as_float(r[j])) : m;
+                }
+            }
+            // pass 2: probabilities (fp16, back into TMEM over the consumed S columns), row sum
+            const float ms = m * scale_log2;
+            float sum = 0.f;
+            for (int c = 0; c < nch; c++) {
+                ptx::tmem_ld_32x32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+                uint32_t pk[16];
+                if (c * 32 + 32 <= L) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float p0 = ex2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms));
+                        const float p1 = ex2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms));
+                        sum += p0 + p1;
+                        pk[j] = pack2(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        float p0 = ex2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms));
+                        float p1 = ex2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms));
+                        p0 = (c * 32 + 2 * j < L) ? p0 : 0.f;
+                        p1 = (c * 32 + 2 * j + 1 < L) ? p1 : 0.f;
+                        sum += p0 + p1;
+                        pk[j] = pack2(p0, p1);
+                    }
+                }
+                ptx::tmem_st_32x16(taddr + c * 16, pk);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_ready);
+            // O = P . V
+            ptx::mbar_wait(o_ready, it & 1);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32(taddr + ATC_O_COL, r);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(t_free);
+            if (q < L) {
+                const float inv = 1.0f / sum;
+                uint4* dst = reinterpret_cast<uint4*>(ctx + static_cast<size_t>(seq_start[s] - row_base + q) * hidden + h * ATC_HD);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; v4++) {
+                    uint4 o;
+                    o.x = pack2(__uint_as_float(r[8 * v4 + 0]) * inv, __uint_as_float(r[8 * v4 + 1]) * inv);
+                    o.y = pack2(__uint_as_float(r[8 * v4 + 2]) * inv, __uint_as_float(r[8 * v4 + 3]) * inv);
+                    o.z = pack2(__uint_as_float(r[8 * v4 + 4]) * inv, __uint_as_float(r[8 * v4 + 5]) * inv);
+                    o.w = pack2(__uint_as_float(r[8 * v4 + 6]) * inv, __uint_as_float(r[8 * v4 + 7]) * inv);
+                    dst[v4] = o;
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, ATC_TMEM_COLS);
+    }
+}
+
+}  // namespace
+
+bool attention_tc_supported(int hidden, int heads, int max_pos) { return hidden / heads == ATC_HD && max_pos <= ATC_MAXL; }
+
+// qkv: head-major [heads][n_tokens][3 * 32] fp16; items: [n_seq * 2] work list + 1 counter behind it
+bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int* items,
+                         int* item_count, int row_base, int n_seq, int n_tokens, int hidden, int heads, __half* ctx,
+                         bool build_items, int num_sms) {
+    if (n_seq <= 0) return true;
+    if (build_items) {  // once per encoder pass: the list is the same for every layer
+        LB2_CUDA_OK(cudaMemsetAsync(item_count, 0, sizeof(int), s));
+        attention_tc_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_len, n_seq, items, item_count);
+        LB2_CUDA_OK(cudaGetLastError());
+    }
+    CUtensorMap tm_qk, tm_v;
+    if (!make_tmap_f16_3d(&tm_qk, qkv, 3 * ATC_HD, n_tokens, heads, 2 * ATC_HD, ATC_BOX) ||
+        !make_tmap_f16_3d(&tm_v, qkv, 3 * ATC_HD, n_tokens, heads, ATC_HD, ATC_BOX))
+        return false;
+    static thread_local int attr_dev_mask[8] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 256 || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
+        LB2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
+    }
+    attention_tc_kernel<<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, seq_start, seq_len, items, item_count, row_base,
+                                                                  heads, hidden, ctx);
+    LB2_CUDA_OK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace lb2

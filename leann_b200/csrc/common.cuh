@@ -24,6 +24,8 @@ enum Epilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RES = 2 };
 // ---- gemm_tcgen05.cu
 bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols = 64);
+bool make_tmap_f16_3d(CUtensorMap* map, const void* ptr, uint64_t row_elems, uint64_t rows, uint64_t groups, uint32_t box_cols,
+                      uint32_t box_rows);
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms, int c_group = 0);
 int gemm_block_n();
@@ -88,5 +90,11 @@ bool launch_layernorm(cudaStream_t s, const __half* in, const float* g, const fl
 bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int* items,
                       int* item_count, int row_base, int max_pos, int n_seq, int n_tokens, int hidden, int heads,
                       __half* ctx, bool build_items);
+
+// ---- attention_tc.cu: tcgen05 attention (head_dim 32, passages <= 256 tokens)
+bool attention_tc_supported(int hidden, int heads, int max_pos);
+bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_start, const int32_t* seq_len, int* items,
+                         int* item_count, int row_base, int n_seq, int n_tokens, int hidden, int heads, __half* ctx,
+                         bool build_items, int num_sms);
 
 }  // namespace lb2

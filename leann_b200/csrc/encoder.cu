@@ -13,6 +13,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lb2 {
@@ -410,6 +412,16 @@ bool launch_attention(cudaStream_t s, const __half* qkv, const int32_t* seq_star
     if (n_seq <= 0) return true;
     const int hd = hidden / heads;
     if (max_pos > 512) { set_error("attention: max_pos %d > 512", max_pos); return false; }
+    // head_dim 32 and passages of at most 256 tokens (all-MiniLM-L6-v2): the tcgen05 kernel (attention_tc.cu).
+    // Other shapes (bge-base: head_dim 64, up to 512 tokens) keep the mma.sync kernel below.
+    static const bool force_legacy = getenv("LB2_ATTN_LEGACY") && atoi(getenv("LB2_ATTN_LEGACY")) != 0;  // A/B profiling only
+    if (!force_legacy && attention_tc_supported(hidden, heads, max_pos)) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return launch_attention_tc(s, qkv, seq_start, seq_len, items, item_count, row_base, n_seq, n_tokens, hidden, heads, ctx,
+                                   build_items, sms);
+    }
     if (build_items) {  // once per encoder pass: the list is the same for every layer
         LB2_CUDA_OK(cudaMemsetAsync(item_count, 0, sizeof(int), s));
         attention_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_len, n_seq, items, item_count);

@@ -313,6 +313,30 @@ bool make_tmap_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
     return true;
 }
 
+// Group-major activation [groups][rows][row_elems] fp16 (the head-major QKV buffer), box = [1][box_rows][box_cols];
+// box_cols = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B (the inner box extent is exactly one swizzle span).
+bool make_tmap_f16_3d(CUtensorMap* map, const void* ptr, uint64_t row_elems, uint64_t rows, uint64_t groups, uint32_t box_cols,
+                      uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return false;
+    }
+    cuuint64_t dims[3] = {row_elems, rows, groups};
+    cuuint64_t strides[2] = {row_elems * 2, rows * row_elems * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3d) failed (%d) rows=%llu groups=%llu", (int)r, (unsigned long long)rows,
+                  (unsigned long long)groups);
+        return false;
+    }
+    return true;
+}
+
 // Output viewed as [groups][rows][group_cols] fp16 (group-major), box = [1][32 rows][32 cols], SWIZZLE_64B.
 static bool make_tmap_f16_grouped(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t group_cols, uint64_t groups) {
     EncodeTiledFn fn = get_encode_fn();

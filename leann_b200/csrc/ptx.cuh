@@ -66,6 +66,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 3D tiled load (c0 innermost).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // 2D tiled store smem -> global (bulk async group); rows/cols outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -118,6 +127,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the A operand read from TENSOR MEMORY (M = 128: TMEM lane = row, 16-bit elements packed two per
+// 32-bit column, element 2c in the low half) and B from shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on `bar` when all previously issued tcgen05.mma of this thread complete.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -136,6 +158,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 16 columns: thread t of the warp writes its 16 registers to TMEM lane (lane_base + t).
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -153,10 +187,24 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     desc |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B   [61,64)
     return desc;
 }
+// MN-major B operand tile (rows = K index, the N elements of a row contiguous), swizzled: what TMA writes for a
+// [K rows] x [N cols] box whose inner extent is exactly one swizzle span (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B).
+// Canonical form ((T,4|8,m),(8,k)) : ((1,T,LBO),(4T|8T,SBO)) (cute/atom/mma_traits_sm100.hpp): SBO = bytes between
+// 8-row groups along K, LBO = bytes between N blocks (one block here).
+__device__ __forceinline__ uint64_t make_mn_major_desc(uint32_t smem_addr, uint32_t row_bytes /* 64 or 128 */) {
+    uint64_t desc = 0;
+    desc |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    desc |= static_cast<uint64_t>(1) << 16;                                   // LBO (unused: N is one block wide)
+    desc |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;                // SBO
+    desc |= static_cast<uint64_t>(1) << 46;                                   // version
+    desc |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;            // SWIZZLE_128B : SWIZZLE_64B
+    return desc;
+}
 // kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 accumulate, both K-major.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;  // B operand is MN-major (bit 16, cute/arch/mma_sm100_desc.hpp)
 
 }  // namespace ptx
 }  // namespace lb2

@@ -2,6 +2,9 @@
 
 * ``VamanaOracle``     : oracle/liboracle.so (vamana_oracle.c), the C restatement of the reference's
                          PQFlashIndex::cached_beam_search as LEANN drives it; travels to the GPU box.
+* ``DiskannFlash``     : oracle/_ref/libleann_ref_diskann_flash.so, the reference's own PQFlashIndex::load +
+                         cached_beam_search compiled from /root/reference (diskann_flash_harness.cpp: in-process file
+                         reader and embedding fetch); the checker that PINS the search loop.
 * ``DiskannPrimitives``: oracle/_ref/libleann_ref_diskann.so, the reference's own NeighborPriorityQueue and
                          FixedChunkPQTable compiled from /root/reference (diskann_ref_harness.cpp); prebuilt in the
                          dev container, the .so travels.
@@ -219,3 +222,48 @@ class DiskannPrimitives:
         self.lib.dref_pq_lookup(_p(ids, C.c_uint32), C.c_uint64(len(ids)), _p(codes, C.c_uint8), C.c_uint64(n_chunks),
                                 _p(np.ascontiguousarray(lut, np.float32), C.c_float), _p(scratch, C.c_uint8), _p(out, C.c_float))
         return out
+
+
+def have_diskann_flash() -> bool:
+    return (HERE / "_ref" / "libleann_ref_diskann_flash.so").exists()
+
+
+class DiskannFlash:
+    """The reference's compiled PQFlashIndex (load + cached_beam_search) over index files on disk.  Arguments follow
+    StaticDiskIndex (python/src/static_disk_index.cpp:15-48, 88-118): index prefix, pq prefix, partition prefix."""
+
+    def __init__(self, index_prefix: str, metric: str, partition_prefix: str = "", pq_prefix: str | None = None, nthreads: int = 1):
+        self.lib = C.CDLL(str(HERE / "_ref" / "libleann_ref_diskann_flash.so"))
+        self.lib.dflash_open.restype = C.c_void_p
+        h = self.lib.dflash_open(str(index_prefix).encode(), str(pq_prefix or index_prefix).encode(), str(partition_prefix).encode(),
+                                 METRICS[metric.lower()], nthreads)
+        if not h:
+            raise RuntimeError(f"reference PQFlashIndex::load failed for {index_prefix}")
+        self.h = C.c_void_p(h)
+        self._emb = None
+
+    def set_embeddings(self, emb):
+        """The table the in-process embedding server answers fetch_embeddings_zmq from."""
+        self._emb = np.ascontiguousarray(emb, np.float32)
+        self.lib.dflash_set_embeddings(_p(self._emb, C.c_float), C.c_int64(self._emb.shape[0]), int(self._emb.shape[1]))
+
+    def search(self, q, k, L=64, beam_width=1, deferred_fetch=False, skip_search_reorder=False, io_limit=0xFFFFFFFF):
+        q = np.ascontiguousarray(q, np.float32)
+        nq, dim = q.shape
+        ids = np.zeros((nq, k), np.uint64)
+        D = np.zeros((nq, k), np.float32)
+        cmps, hops, ios = (np.zeros(nq, np.uint32) for _ in range(3))
+        if deferred_fetch and self._emb is not None:  # the table is process-global: re-point it at this instance's
+            self.lib.dflash_set_embeddings(_p(self._emb, C.c_float), C.c_int64(self._emb.shape[0]), int(self._emb.shape[1]))
+        rc = self.lib.dflash_search(self.h, _p(q, C.c_float), C.c_int64(nq), dim, C.c_int64(k), C.c_int64(L), C.c_int64(beam_width),
+                                    int(deferred_fetch), int(skip_search_reorder), C.c_uint32(io_limit), _p(ids, C.c_uint64),
+                                    _p(D, C.c_float), _p(cmps, C.c_uint32), _p(hops, C.c_uint32), _p(ios, C.c_uint32))
+        if rc:
+            raise RuntimeError("reference cached_beam_search failed")
+        return D, ids.astype(np.int64), dict(n_cmps=cmps.astype(np.int64), n_hops=hops.astype(np.int64), n_ios=ios.astype(np.int64))
+
+    def __del__(self):
+        try:
+            self.lib.dflash_close(self.h)
+        except Exception:
+            pass

@@ -7,11 +7,14 @@
  *   (USE_DEFERRED_FETCH), the expanded nodes are re-scored once at the end from freshly computed embeddings.
  * All file:line citations are under /root/reference/packages/leann-backend-diskann/third_party/DiskANN/.
  *
- * PARITY STATUS: pq_flash_index.cpp cannot be compiled here (libaio, protobuf, Boost, MKL), so the search LOOP below is
- * an unpinned restatement of src/pq_flash_index.cpp:1779-2906.  Its primitives ARE pinned: the queue
- * (include/neighbor.h:39-152) and the PQ arithmetic (src/pq.cpp:180-340) are checked operation by operation
- * against the reference's own code compiled into oracle/_ref/libleann_ref_diskann.so
- * (tests/test_vamana_oracle.py).
+ * PARITY STATUS: PINNED.  The search loop below restates src/pq_flash_index.cpp:1779-2906 and is checked against the
+ * reference's own PQFlashIndex::load + cached_beam_search compiled from that file (oracle/_ref/
+ * libleann_ref_diskann_flash.so, diskann_flash_harness.cpp: declaration-only stand-ins for libaio / Boost / the protoc
+ * header, in-process file reader and embedding fetch): identical ids, hop / I/O / comparison counts and distances within
+ * 2e-5 on the committed fixtures (outputs of the compiled reference are stored in tests/golden/vamana_small_expected.npz)
+ * and on fresh indexes of both file layouts, l2 / mips / cosine, beam widths 1-8, io_limit (tests/test_vamana_oracle.py).
+ * Its primitives are additionally pinned operation by operation: the queue (include/neighbor.h:39-152) and the PQ
+ * arithmetic (src/pq.cpp:180-340) against oracle/_ref/libleann_ref_diskann.so.
  *
  * Two deliberate choices, both inside the 1e-3 distance tolerance and both shared with the CUDA path so ids match
  * bit for bit: (1) full-precision distances use the canonical lane-strided fp32 order of canon_dist.h instead of the

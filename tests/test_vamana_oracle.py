@@ -7,9 +7,11 @@ import pytest
 
 from leann_b200 import diskann_format as dfmt
 from leann_b200.vamana_build import build_diskann_index, build_vamana_graph
-from oracle.vamana_binding import DiskannPrimitives, OracleQueue, VamanaOracle, have_diskann_reference
+from oracle.vamana_binding import (DiskannFlash, DiskannPrimitives, OracleQueue, VamanaOracle, have_diskann_flash,
+                                   have_diskann_reference)
 
 needs_ref = pytest.mark.skipif(not have_diskann_reference(), reason="compiled DiskANN primitives not present")
+needs_flash = pytest.mark.skipif(not have_diskann_flash(), reason="compiled PQFlashIndex (oracle/_ref/libleann_ref_diskann_flash.so) not present")
 
 
 def unit_rows(n, d, seed, clusters=12):
@@ -256,3 +258,80 @@ def test_vamana_builder_degree_and_connectivity():
         nxt = g.nbrs[frontier].ravel(); nxt = np.unique(nxt[nxt >= 0]); nxt = nxt[~seen[nxt]]
         seen[nxt] = True; frontier = list(nxt)
     assert seen.mean() > 0.99
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The search loop, PINNED: oracle/vamana_oracle.c against the reference's own PQFlashIndex::cached_beam_search
+# (pq_flash_index.cpp:1779-2906, compiled from /root/reference into oracle/_ref/libleann_ref_diskann_flash.so).
+def _expanded_degree_sum(g, full_ids, n_full):
+    deg = g.degrees().astype(np.int64)
+    return np.array([deg[full_ids[i, : n_full[i]]].sum() for i in range(len(n_full))], np.int64)
+
+
+def _check_against_reference(o, G, q, k, L, beam, kw, rD, rI, rs, tag):
+    D, I, info = o.search(q, k, L=L, beam_width=beam, **kw)
+    # slots beyond the number of expanded nodes: the reference leaves whatever its scratch vector held (it copies k entries
+    # of full_retset regardless, :2861-2872); the restatement and the C ABI define them as (-1, FLT_MAX)
+    filled = np.arange(k)[None, :] < info["n_full"][:, None]
+    assert np.array_equal(I[filled], rI[filled]), tag                        # identical ids, position by position
+    assert (I[~filled] == -1).all(), tag
+    assert np.abs(D[filled] - rD[filled]).max() <= 2e-5 * max(1.0, float(np.abs(rD[filled]).max())), (tag, float(np.abs(D - rD)[filled].max()))
+    assert np.array_equal(info["n_hops"], rs["n_hops"]) and np.array_equal(info["n_full"], rs["n_ios"]), tag
+    # QueryStats.n_cmps counts every PQ-scored neighbour of an expanded node plus every first visit (:2578, :2599);
+    # the oracle's cmps is the local counter of first visits (:2596)
+    assert np.array_equal(info["cmps"] + _expanded_degree_sum(G["g"], info["full_ids"], info["n_full"]), rs["n_cmps"]), tag
+
+
+@pytest.mark.parametrize("metric", ["mips", "l2"])
+def test_oracle_matches_the_committed_outputs_of_the_compiled_reference(golden_dir, metric):
+    """Runs everywhere (no compiled reference needed): the *_ref* arrays of vamana_small_expected.npz were produced by the
+    reference's compiled cached_beam_search over the committed index files (tests/golden/make_vamana_golden.py)."""
+    from helpers import VAMANA_GOLDEN_CASES, load_vamana_golden
+    G = load_vamana_golden(golden_dir, metric)
+    o = VamanaOracle(G["g"], G["pq"], G["codes"], metric, G["max_norm"])
+    for L, beam, k in VAMANA_GOLDEN_CASES:
+        for mode, kw in (("stored", dict(coords=G["coords"])), ("deferred", dict(emb=G["emb"])), ("pq", dict(skip_search_reorder=True))):
+            key = f"{metric}_L{L}_b{beam}_k{k}_{mode}"
+            rs = dict(n_cmps=G["exp"][key + "_refcmps"], n_hops=G["exp"][key + "_refhops"], n_ios=G["exp"][key + "_refios"])
+            _check_against_reference(o, G, G["q"], k, L, beam, kw, G["exp"][key + "_refD"], G["exp"][key + "_refI"], rs, key)
+
+
+@needs_flash
+@pytest.mark.parametrize("metric", ["mips", "l2"])
+def test_compiled_reference_reproduces_its_committed_outputs(golden_dir, metric):
+    from helpers import VAMANA_GOLDEN_CASES, load_vamana_golden
+    G = load_vamana_golden(golden_dir, metric)
+    for part in ("", G["prefix"]):
+        ref = DiskannFlash(G["prefix"], metric, partition_prefix=part)
+        ref.set_embeddings(G["emb"])
+        for L, beam, k in VAMANA_GOLDEN_CASES:
+            for mode in ("deferred", "pq") + (("stored",) if not part else ()):
+                key = f"{metric}_L{L}_b{beam}_k{k}_{mode}"
+                D, I, st = ref.search(G["q"], k, L=L, beam_width=beam, deferred_fetch=(mode == "deferred"), skip_search_reorder=(mode == "pq"))
+                assert np.array_equal(I, G["exp"][key + "_refI"]) and np.array_equal(D, G["exp"][key + "_refD"]), key
+                assert np.array_equal(st["n_cmps"], G["exp"][key + "_refcmps"]) and np.array_equal(st["n_hops"], G["exp"][key + "_refhops"])
+
+
+@needs_flash
+@pytest.mark.parametrize("metric,R,n_chunks,dim", [("l2", 16, 12, 48), ("mips", 24, 10, 40), ("cosine", 12, 8, 32), ("mips", 32, 17, 51)])
+def test_compiled_reference_search_loop_pins_the_oracle_on_fresh_indexes(tmp_path, metric, R, n_chunks, dim):
+    """Fresh random indexes (both file layouts), beam widths 1..8, tiny and huge L, io_limit: the restatement follows the
+    compiled reference expansion for expansion (hops, I/Os, comparison counts) and returns the same ids."""
+    emb = unit_rows(2500, dim, 11 + R)
+    emb *= np.random.default_rng(5).uniform(0.6, 1.4, (len(emb), 1)).astype(np.float32)
+    prefix, g, coords, pq, codes, max_norm = build_diskann_index(tmp_path, "f", emb, metric=metric, R=R, n_chunks=n_chunks,
+                                                                 partition=True, keep_disk_index=True, device="cpu")
+    G = dict(g=g)
+    q = unit_rows(16, dim, 99)
+    o = VamanaOracle(g, pq, codes, metric, max_norm)
+    for part in ("", prefix):
+        ref = DiskannFlash(prefix, metric, partition_prefix=part)
+        ref.set_embeddings(emb)
+        for L, beam, k, io_limit in ((64, 1, 10, 2 ** 32 - 1), (10, 2, 10, 2 ** 32 - 1), (150, 4, 20, 2 ** 32 - 1), (64, 8, 5, 2 ** 32 - 1),
+                                     (64, 2, 10, 7), (32, 1, 3, 1)):
+            for mode, kw in (("deferred", dict(emb=emb)), ("pq", dict(skip_search_reorder=True))) + \
+                            ((("stored", dict(coords=coords)),) if not part else ()):
+                rD, rI, rs = ref.search(q, k, L=L, beam_width=beam, deferred_fetch=(mode == "deferred"),
+                                        skip_search_reorder=(mode == "pq"), io_limit=io_limit)
+                _check_against_reference(o, G, q, k, L, beam, dict(kw, io_limit=io_limit), rD, rI, rs,
+                                         f"{metric} R{R} L{L} b{beam} k{k} io{io_limit} {mode} {'partition' if part else 'standard'}")
