@@ -1,15 +1,19 @@
 #!/bin/bash
-# round 2, session 1: graph-build kernels + bench harness at 1 M and 10 M
+# round 2, session 1: graph-build kernels, tcgen05 attention, bench harness at 1 M and 10 M
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 O=gpurun_out/r2s1
 nvidia-smi --query-gpu=name,memory.total --format=csv > $O.gpu.txt; nproc >> $O.gpu.txt; free -g >> $O.gpu.txt; df -h /tmp >> $O.gpu.txt
-timeout 600 python -m pytest tests/test_gpu_graph_build.py -x -q -s > $O.test_build.log 2>&1; echo "test_build rc=$?" 
+python -c "from leann_b200 import build; build.build()" > $O.build.log 2>&1
+timeout 300 python scripts/attn_debug.py > $O.attn_debug.log 2>&1; echo "attn_debug rc=$?"; grep "==\|####" $O.attn_debug.log | head -60
+timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -k attention > $O.test_attn.log 2>&1; arc=$?; echo "test_attn rc=$arc"; tail -3 $O.test_attn.log
+if [ $arc -ne 0 ]; then export LB2_ATTN_LEGACY=1; echo "USING LEGACY ATTENTION for the rest"; fi
+timeout 600 python -m pytest tests/test_gpu_graph_build.py -x -q -s > $O.test_build.log 2>&1; echo "test_build rc=$?"
 tail -5 $O.test_build.log
 export LB2_BENCH_VERBOSE=1
 timeout 900 python bench.py --chunks 1000000 --steps 3 --warmup 3 --budget-s 60 --no-cpu-baseline > $O.bench_1m.json 2> $O.bench_1m.err; echo "bench1m rc=$?"
 grep "\[bench\]" $O.bench_1m.err | tail -12; python -c "
-import json;d=json.load(open('$O.bench_1m.json'));print({k:d[k] for k in ('value','recall_at_10')}, d['e2e']['value'], d['detail']['world'])"
+import json;d=json.load(open('$O.bench_1m.json'));print({k:d[k] for k in ('value','recall_at_10')}, d['e2e']['value'], d['detail']['attention_share'], d['detail']['world'])"
 timeout 1500 python bench.py --steps 3 --warmup 3 --budget-s 80 --no-cpu-baseline > $O.bench_10m.json 2> $O.bench_10m.err; echo "bench10m rc=$?"
 grep "\[bench\]\|inserted" $O.bench_10m.err | tail -40; python -c "
-import json;d=json.load(open('$O.bench_10m.json'));print({k:d[k] for k in ('value','recall_at_10')}, d['e2e']['value'], d['detail']['world'])"
+import json;d=json.load(open('$O.bench_10m.json'));print({k:d[k] for k in ('value','recall_at_10')}, d['e2e']['value'], d['detail']['attention_share'], d['detail']['world'])"

@@ -19,10 +19,12 @@ def test_encoder_matches_fp32_bert(lib, cuda_ok, preset, n):
     ref = EncoderOracle(preset, w).encode_store(corpus.tokens, corpus.offsets)
     assert np.isfinite(E).all()
     assert np.allclose(np.linalg.norm(E, axis=1), 1, atol=1e-4)
-    assert np.abs(E - ref).max() < 2e-3, np.abs(E - ref).max()
     # what the traversal consumes: distances -E.q  (hnsw_embedding_server.py:195-200), tolerance of north_star
     q = ref[:8]
-    assert np.abs(E @ q.T - ref @ q.T).max() < 1e-3
+    dE, dD = float(np.abs(E - ref).max()), float(np.abs(E @ q.T - ref @ q.T).max())
+    print(f"{preset.name}: max |dE| = {dE:.2e} (bound 2e-3), max |d distance| = {dD:.2e} (bound 1e-3)")
+    assert dE < 2e-3, dE
+    assert dD < 1e-3, dD
 
 
 def test_encoding_is_batch_and_position_independent(lib, cuda_ok):
@@ -89,3 +91,70 @@ def test_embedding_server_shim_serves_gpu_embeddings(lib, cuda_ok):
         ctx.term()
         th.join(5)
         idx.close()
+
+
+def _realistic_bert(preset, seed=0):
+    """A transformers.BertModel with the statistics trained checkpoints have and N(0, 0.02) initialisation lacks (no
+    checkpoint can be downloaded here): a few "massive activation" channels in the embeddings (x30), LayerNorm gains
+    spread over 0.3..5 with large values on the outlier channels, non-zero LayerNorm biases, heavier-tailed linear weights."""
+    import torch
+    from transformers import BertConfig, BertModel
+
+    cfg = BertConfig(vocab_size=preset.vocab_size, hidden_size=preset.hidden, num_hidden_layers=preset.layers,
+                     num_attention_heads=preset.heads, intermediate_size=preset.ffn, hidden_act="gelu",
+                     max_position_embeddings=preset.max_pos, type_vocab_size=preset.type_vocab, layer_norm_eps=preset.ln_eps,
+                     hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    try:
+        cfg._attn_implementation = "eager"
+    except Exception:
+        pass
+    torch.manual_seed(seed)
+    m = BertModel(cfg, add_pooling_layer=False).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    outliers = torch.randperm(preset.hidden, generator=g)[:4]
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if "LayerNorm.weight" in name:
+                p.copy_(torch.exp(torch.randn(p.shape, generator=g) * 0.45).clamp(0.3, 5.0))
+                p[outliers] = 5.0
+            elif "LayerNorm.bias" in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+            elif "word_embeddings" in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+                p[:, outliers] *= 30.0
+            elif name.endswith("dense.weight") or "self." in name and name.endswith("weight"):
+                w = torch.randn(p.shape, generator=g) * 0.035
+                w *= torch.exp(torch.randn(p.shape[0], 1, generator=g) * 0.3)  # per-output-row scale spread
+                p.copy_(w)
+            elif name.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    return m
+
+
+def test_hf_checkpoint_path_with_realistic_weight_statistics(lib, cuda_ok):
+    """backend.weights_from_hf (the loader a real sentence-transformers checkpoint goes through) -> GPU encoder, against
+    the SAME transformers model evaluated in fp32 (masked mean pool + L2 normalisation, embedding_compute.py:319-335)."""
+    import torch
+    from leann_b200.backend import weights_from_hf
+
+    preset0 = synth.MINILM_L6
+    hf = _realistic_bert(preset0)
+    preset, blob = weights_from_hf(hf, preset0.name)
+    assert (preset.hidden, preset.layers, preset.heads, preset.ffn, preset.max_pos, preset.pooling) == (384, 6, 12, 1536, 256, 0)
+    n = 64
+    _, corpus = synth.make_corpus(n, preset.vocab_size, seed=21, max_len=preset.max_pos)
+    idx = open_encoder_only(preset, blob, corpus)
+    E = idx.encode_ids(np.arange(n))
+    ref = []
+    with torch.inference_mode():
+        for i in range(n):
+            ids = torch.from_numpy(corpus.passage(i)[: preset.max_pos].astype(np.int64))[None]
+            h = hf(input_ids=ids, attention_mask=torch.ones_like(ids)).last_hidden_state[0]
+            ref.append(torch.nn.functional.normalize(h.mean(0), dim=0).numpy())
+    ref = np.stack(ref)
+    dE = float(np.abs(E - ref).max())
+    dD = float(np.abs(E @ ref[:16].T - ref @ ref[:16].T).max())
+    print(f"realistic-statistics weights: max |dE| = {dE:.2e}, max |d distance| = {dD:.2e}, cos >= {float((E * ref).sum(1).min()):.6f}")
+    assert np.isfinite(E).all()
+    assert dD < 1e-3, (dE, dD)  # north_star: distances within 1e-3
+    assert dE < 2e-3, dE
