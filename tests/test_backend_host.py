@@ -136,3 +136,36 @@ def test_diskann_builder_writes_the_reference_file_set_and_search_fails_loudly_w
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CUDA device|no CPU path"):
             s.search(q, 5, recompute_embeddings=False, skip_search_reorder=True)
+
+
+def test_token_store_equals_the_reference_tokenizer_call(tmp_path):
+    """the uint16 sidecars written once by tokenize_passages hold exactly the ids the reference's
+    per-hop tokenizer call produces (embedding_compute.py:299-305: hf_tokenizer(batch, padding=True, truncation=True,
+    max_length=...)) once padding is stripped by the attention mask — WordPiece, [CLS]/[SEP], truncation included.
+    The vocabulary is built locally (no checkpoint on disk); the tokenizer classes are the real ones."""
+    from tokenizers import BertWordPieceTokenizer
+    from transformers import PreTrainedTokenizerFast
+
+    from leann_b200.backend import tokenize_passages
+
+    words = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "the", "quick", "brown", "fox", "##es", "jump", "##s", "over", "lazy",
+             "dog", ".", ",", "pride", "and", "prejudice", "un", "##believ", "##able", "it", "is", "a", "truth", "##ly"]
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(words))
+    tok = PreTrainedTokenizerFast(tokenizer_object=BertWordPieceTokenizer(str(vf), lowercase=True)._tokenizer, unk_token="[UNK]",
+                                  pad_token="[PAD]", cls_token="[CLS]", sep_token="[SEP]", mask_token="[MASK]")
+    texts = ["The quick brown foxes jumps over the lazy dog.", "Pride and Prejudice", "unbelievable, truthly unbelievable zebra",
+             "it is a truth " * 40, "."]
+    max_len = 24
+    tokenize_passages(str(tmp_path / "t.leann"), texts, tok, max_len)
+    toks = np.load(tmp_path / "t.leann.tokens.npy")
+    offs = np.load(tmp_path / "t.leann.tokoffsets.npy")
+    assert toks.dtype == np.uint16 and offs.dtype == np.uint64 and len(offs) == len(texts) + 1
+    ref = tok(texts, padding=True, truncation=True, max_length=max_len, return_tensors="np")  # the reference's call
+    for i in range(len(texts)):
+        want = ref["input_ids"][i][ref["attention_mask"][i] == 1]
+        got = toks[int(offs[i]): int(offs[i + 1])]
+        assert np.array_equal(got, want), (i, got, want)
+        assert got[0] == 2 and got[-1] == 3 and len(got) <= max_len  # [CLS] ... [SEP], truncated like the reference
+    with pytest.raises(ValueError):  # ids that do not fit the uint16 store are refused, never wrapped
+        tokenize_passages(str(tmp_path / "u.leann"), ["x"], lambda t, truncation, max_length: {"input_ids": [101, 70000, 102]}, 8)
