@@ -34,6 +34,11 @@ class _LboGraph(C.Structure):
                 ("entry_point", C.c_int), ("max_level", C.c_int), ("vectors", C.POINTER(C.c_float))]
 
 
+class _LboPq(C.Structure):
+    _fields_ = [("ndims", C.c_int), ("n_chunks", C.c_int), ("tables_tr", C.POINTER(C.c_float)), ("centroid", C.POINTER(C.c_float)),
+                ("chunk_offsets", C.POINTER(C.c_uint32)), ("codes", C.POINTER(C.c_uint8))]
+
+
 def _wrap_cb(fn, d):
     """fn(q: np.ndarray[d], ids: np.ndarray[int64]) -> np.ndarray[float32]"""
     if fn is None:
@@ -75,7 +80,19 @@ class Oracle:
                             graph.entry_point, graph.max_level,
                             _p(self.vectors, C.c_float) if self.vectors is not None else None)
 
-    def search(self, q, k, ef=64, beam=1, batch_size=0, check_rel=True, dist_fn=None, nthreads=1):
+    def set_pq(self, pq, codes):
+        """PQ pruning data (HNSW::load_pq_pruning_data, impl/HNSW_search.cpp:253-297): pq = diskann_format.PQTable
+        (pivots [256, ndims], centroid, chunk_offsets), codes [ntotal, n_chunks] uint8."""
+        self._pq_keep = dict(tables_tr=np.ascontiguousarray(np.asarray(pq.pivots, np.float32).T),  # [ndims, 256]
+                             centroid=np.ascontiguousarray(pq.centroid, np.float32).reshape(-1),
+                             chunk_offsets=np.ascontiguousarray(pq.chunk_offsets, np.uint32).reshape(-1),
+                             codes=np.ascontiguousarray(codes, np.uint8))
+        k = self._pq_keep
+        self.cpq = _LboPq(int(pq.ndims), int(pq.n_chunks), _p(k["tables_tr"], C.c_float), _p(k["centroid"], C.c_float),
+                          _p(k["chunk_offsets"], C.c_uint32), _p(k["codes"], C.c_uint8))
+
+    def search(self, q, k, ef=64, beam=1, batch_size=0, check_rel=True, dist_fn=None, nthreads=1, prune_ratio=0.0,
+               local_prune=False, send_ratio=0.0):
         q = np.ascontiguousarray(q, np.float32)
         nq = q.shape[0]
         D = np.empty((nq, k), np.float32)
@@ -83,9 +100,12 @@ class Oracle:
         ndis = np.zeros(nq, np.int64)
         nhops = np.zeros(nq, np.int64)
         cb = _wrap_cb(dist_fn, self.g.d)
-        rc = self.lib.lbo_search(C.byref(self.cg), C.c_int64(nq), _p(q, C.c_float), int(k), int(ef), int(beam),
-                                 int(batch_size), int(bool(check_rel)), _p(D, C.c_float), _p(I, C.c_int64),
-                                 _p(ndis, C.c_int64), _p(nhops, C.c_int64), cb, None, int(nthreads))
+        cpq = getattr(self, "cpq", None)
+        rc = self.lib.lbo_search_pq(C.byref(self.cg), C.c_int64(nq), _p(q, C.c_float), int(k), int(ef), int(beam),
+                                    int(batch_size), int(bool(check_rel)), _p(D, C.c_float), _p(I, C.c_int64),
+                                    _p(ndis, C.c_int64), _p(nhops, C.c_int64), cb, None, int(nthreads),
+                                    C.byref(cpq) if cpq is not None else None, C.c_float(prune_ratio), int(bool(local_prune)),
+                                    C.c_float(send_ratio))
         if rc != 0:
             raise RuntimeError("lbo_search failed (no vectors and no callback?)")
         return D, I, ndis, nhops
@@ -160,7 +180,13 @@ class Reference:
             ef_construction=lib.ref_ef_construction(h), ef_search=lib.ref_ef_search(h),
         )
 
-    def search(self, q, k, ef=64, beam=1, batch_size=0, check_rel=True, dist_fn=None, nthreads=1):
+    def load_pq(self, pivots_path, compressed_path):
+        """HNSW::load_pq_pruning_data (impl/HNSW_search.cpp:253-297) on DiskANN-format PQ files."""
+        if self.lib.ref_load_pq(self.h, str(pivots_path).encode(), str(compressed_path).encode()) != 0:
+            raise RuntimeError("reference load_pq_pruning_data failed")
+
+    def search(self, q, k, ef=64, beam=1, batch_size=0, check_rel=True, dist_fn=None, nthreads=1, prune_ratio=0.0,
+               local_prune=False, send_ratio=0.0):
         q = np.ascontiguousarray(q, np.float32)
         nq = q.shape[0]
         D = np.empty((nq, k), np.float32)
@@ -168,9 +194,10 @@ class Reference:
         ndis = np.zeros(nq, np.int64)
         nhops = np.zeros(nq, np.int64)
         cb = _wrap_cb(dist_fn, self.d)
-        rc = self.lib.ref_search(self.h, C.c_int64(nq), _p(q, C.c_float), C.c_int64(k), int(ef), int(beam),
-                                 int(batch_size), int(bool(check_rel)), _p(D, C.c_float), _p(I, C.c_int64),
-                                 _p(ndis, C.c_int64), _p(nhops, C.c_int64), cb, None, int(nthreads))
+        rc = self.lib.ref_search_pq(self.h, C.c_int64(nq), _p(q, C.c_float), C.c_int64(k), int(ef), int(beam),
+                                    int(batch_size), int(bool(check_rel)), C.c_float(prune_ratio), int(bool(local_prune)),
+                                    C.c_float(send_ratio), _p(D, C.c_float), _p(I, C.c_int64),
+                                    _p(ndis, C.c_int64), _p(nhops, C.c_int64), cb, None, int(nthreads))
         if rc != 0:
             raise RuntimeError("ref_search failed")
         return D, I, ndis, nhops

@@ -222,6 +222,62 @@ int ref_search(void* h, int64_t nq, const float* q, int64_t k, int ef, int beam_
     return 0;
 }
 
+// PQ-guided pruning (impl/HNSW_search.cpp:442-465, 645-750): the reference only prunes after
+// HNSW::load_pq_pruning_data (:253-297) has read DiskANN-style pivots + compressed codes.
+int ref_load_pq(void* h, const char* pivots_path, const char* compressed_path) {
+    return ((RefIndex*)h)->hnsw.load_pq_pruning_data(pivots_path, compressed_path) ? 0 : -1;
+}
+
+// ref_search with the three pruning knobs of SearchParametersHNSW (impl/HNSW.h:54-73)
+int ref_search_pq(void* h, int64_t nq, const float* q, int64_t k, int ef, int beam_size, int batch_size,
+                  int check_relative_distance, float pq_pruning_ratio, int local_prune, float send_neigh_times_ratio,
+                  float* D, int64_t* I, int64_t* ndis, int64_t* nhops, ref_dist_cb cb, void* ctx, int nthreads) {
+    RefIndex* R = (RefIndex*)h;
+    const HNSW& hnsw = R->hnsw;
+    if (!cb && !R->vectors) return -1;
+    faiss::SearchParametersHNSW params;
+    params.efSearch = ef;
+    params.beam_size = beam_size;
+    params.batch_size = batch_size;
+    params.check_relative_distance = check_relative_distance != 0;
+    params.pq_pruning_ratio = pq_pruning_ratio;
+    params.local_prune = local_prune != 0;
+    params.send_neigh_times_ratio = send_neigh_times_ratio;
+    using RH = faiss::HeapBlockResultHandler<HNSW::C>;
+    RH bres((size_t)nq, D, I, (size_t)k);
+    if (nthreads < 1) nthreads = 1;
+    int64_t ntotal = (int64_t)hnsw.levels.size();
+    int rc = 0;
+#pragma omp parallel num_threads(nthreads) if (nthreads > 1 && nq > 1)
+    {
+        faiss::VisitedTable vt((int)ntotal);
+        RH::SingleResultHandler res(bres);
+        std::unique_ptr<faiss::DistanceComputer> dc;
+        if (cb)
+            dc.reset(new CallbackDC(cb, ctx));
+        else
+            dc.reset(new FlatDC(R->vectors, R->d, R->ip));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t i = 0; i < nq; i++) {
+            res.begin((size_t)i);
+            dc->set_query(q + (size_t)i * R->d);
+            try {
+                faiss::HNSWStats st = hnsw.search(*dc, res, vt, &params, nullptr);
+                if (ndis) ndis[i] = (int64_t)st.ndis;
+                if (nhops) nhops[i] = (int64_t)st.nhops;
+            } catch (const std::exception& e) {
+                fprintf(stderr, "ref_search_pq: %s\n", e.what());
+                rc = -2;
+            }
+            res.end();
+        }
+    }
+    if (R->ip) {
+        for (int64_t i = 0; i < nq * k; i++) D[i] = -D[i];
+    }
+    return rc;
+}
+
 // MinimaxHeap exports (impl/HNSW.cpp:1263-1509) for unit-level pinning of the oracle's heap.
 void* ref_mmh_new(int n) { return new HNSW::MinimaxHeap(n); }
 void ref_mmh_free(void* p) { delete (HNSW::MinimaxHeap*)p; }

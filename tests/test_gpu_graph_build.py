@@ -138,3 +138,30 @@ def test_incremental_builder_matches_the_exact_builder(tmp_path):
     r_inc = _recall_with_product_search(g_inc, x, q, gt, tmp_path, "inc")
     print(f"recall@10 ef=64: exact builder {r_exact:.3f}, insertion builder {r_inc:.3f}, mean degree {deg.mean():.1f}")
     assert r_inc > r_exact - 0.03 and r_inc > 0.9
+
+
+def test_incremental_builder_against_the_reference_builder(tmp_path):
+    """Same points, same levels' distribution, same M / efConstruction: the graph from the GPU insertion builder and the graph
+    from the reference's own HNSW::add_with_locks (compiled, oracle/_ref), both searched with the product's stored-vector
+    traversal at efSearch 64.  Construction is order- and thread-dependent in the reference too, so the comparison is on
+    what the graph is for: recall, and the work a search does on it."""
+    from oracle.binding import Reference, export_to_csr, have_reference
+
+    if not have_reference():
+        pytest.skip("compiled reference not present")
+    from leann_b200.graph_build import build_hnsw_graph_incremental
+
+    n, d, M, efc = 100_000, 64, 16, 100
+    x = clustered(n, d, 1000, 5)
+    q = x[:1000] + 0.05 * np.random.default_rng(6).normal(size=(1000, d)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    gt = torch.topk(torch.from_numpy(q).cuda() @ torch.from_numpy(x).cuda().T, 10, dim=1).indices.cpu().numpy()
+    ref = Reference(d, M, True)
+    ref.build(x, ef_construction=efc, nthreads=32)
+    g_ref = export_to_csr(ref.export())
+    g_inc = build_hnsw_graph_incremental(x, M=M, metric="mips", device="cuda", ef_construction=efc)
+    r_ref = _recall_with_product_search(g_ref, x, q, gt, tmp_path, "ref")
+    r_inc = _recall_with_product_search(g_inc, x, q, gt, tmp_path, "inc")
+    print(f"recall@10 ef=64: reference builder {r_ref:.3f} ({g_ref.neighbors.size / n:.1f} links/node), "
+          f"GPU insertion builder {r_inc:.3f} ({g_inc.neighbors.size / n:.1f} links/node)")
+    assert r_inc > r_ref - 0.02
