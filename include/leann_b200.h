@@ -18,6 +18,9 @@
  *   lb2_encode_ids      embedding-server "ids -> embeddings" branch   hnsw_embedding_server.py:213-284
  *   lb2_encode_tokens   embedding-server "texts -> embeddings" branch hnsw_embedding_server.py:134-145
  *                         (compute_query_embedding, leann-core/src/leann/searcher_base.py:86-128)
+ *   lb2_load_pq_pruning HNSW::load_pq_pruning_data(pq_pivots_path, pq_compressed_path)
+ *                         faiss/impl/HNSW_search.cpp:253-297 (DiskANN-format PQ files; enables the PQ-guided pruning
+ *                         branch of search_from_candidates, :442-465, 645-750)
  *   lb2_close           Index destructor / EmbeddingServerManager.stop_server
  *   lb2_last_error      FaissException text surfaced as Python RuntimeError by SWIG
  *
@@ -51,9 +54,9 @@ typedef struct {
     int32_t beam_size;               /* "beam_width"; candidates expanded per hop; default 1       */
     int32_t batch_size;              /* expand until >= batch_size neighbours gathered; 0 = off    */
     int32_t check_relative_distance; /* stop rule of HNSW_search.cpp:583-592; default 1            */
-    float pq_pruning_ratio;          /* "prune_ratio"; must be 0 (PQ pruning: SURVEY 8f row 3)     */
-    int32_t local_prune;             /* must be 0                                                  */
-    float send_neigh_times_ratio;    /* must be 0                                                  */
+    float pq_pruning_ratio;          /* "prune_ratio": share of PQ-ranked candidates NOT scored exactly; like the     */
+    int32_t local_prune;             /* reference, the three pruning knobs act only after lb2_load_pq_pruning()       */
+    float send_neigh_times_ratio;    /* ("local" / "proportional" strategies; default strategy = global queue)        */
     int32_t recompute;               /* 1: recompute embeddings on the GPU (default); 0: stored    */
 } lb2_search_params;
 
@@ -117,6 +120,10 @@ int lb2_set_passages(lb2_index* idx, const uint16_t* tokens, const uint64_t* off
  *   per layer: w_qkv[3H,H] (q,k,v rows stacked) b_qkv[3H] w_o[H,H] b_o[H] ln1_g[H] ln1_b[H]
  *              w_1[F,H] b_1[F] w_2[H,F] b_2[H] ln2_g[H] ln2_b[H]
  * Stored on the device as fp16 matrices / fp32 vectors (the reference loads fp16 too). */
+/* PQ-guided pruning tables: DiskANN-format <prefix>_pq_pivots.bin / <prefix>_pq_compressed.bin over the index's
+ * vectors (MIPS-extended: ndims = d + 1).  Without this call prune_ratio / pruning_strategy are ignored, as in the reference. */
+int lb2_load_pq_pruning(lb2_index* idx, const char* pq_pivots_path, const char* pq_compressed_path);
+
 size_t lb2_encoder_weight_count(const lb2_encoder_config* cfg);
 int lb2_set_encoder(lb2_index* idx, const lb2_encoder_config* cfg, const float* weights, size_t n_floats);
 
@@ -238,9 +245,11 @@ int lb2_build_insert_search(const void* d_x_f16, int64_t n, int32_t d, int32_t m
                             float* d_out_dist, void* d_workspace, size_t workspace_bytes);
 size_t lb2_build_workspace_bytes(int32_t ef, int32_t cap0);
 /* pd: [b, K, K] pairwise candidate distances (fp16, or fp32 when pd_is_f32); dn: [b, K] node-to-candidate distances,
- * ascending; cand: [b, K] ids, -1 padded at the end; out: [b, keep] kept ids / distances, (-1, FLT_MAX) padded. */
+ * ascending; cand: [b, K] ids, -1 padded at the end; out: [b, keep] kept ids / distances, (-1, FLT_MAX) padded.
+ * fill (0..keep): lists shorter than that are topped up with the nearest rejected candidates (the reference's
+ * keep_max_size_level0 branch with a settable floor; 0 = the default behaviour). */
 int lb2_build_select(const void* d_pd, int32_t pd_is_f32, const float* d_dn, const int32_t* d_cand, int64_t b, int32_t K,
-                     int32_t keep, int32_t* d_out_ids, float* d_out_dist);
+                     int32_t keep, int32_t fill, int32_t* d_out_ids, float* d_out_dist);
 
 /* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
 int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,

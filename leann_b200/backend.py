@@ -254,6 +254,10 @@ class B200HnswSearcher(_B200SearcherBase):
             self._index.configure(int(t.get("slots", 0)), int(t.get("passages_per_pass", 0)))
         if t.get("dedup_scope") is not None:  # "hop" (default) | "call"
             self._index.set_option("dedup_scope", {"hop": 0, "call": 1}[str(t["dedup_scope"])])
+        # PQ-guided pruning tables (HNSW::load_pq_pruning_data, HNSW_search.cpp:253-297): DiskANN-format sidecars
+        self._has_pq = self._sidecar("pq_pivots.bin").exists() and self._sidecar("pq_compressed.bin").exists()
+        if self._has_pq:
+            self._index.load_pq_pruning(str(self._sidecar("pq_pivots.bin")), str(self._sidecar("pq_compressed.bin")))
 
     def search(self, query: np.ndarray, top_k: int, zmq_port: Optional[int] = None, complexity: int = 64,
                beam_width: int = 1, prune_ratio: float = 0.0, recompute_embeddings: bool = True,
@@ -279,7 +283,7 @@ class B200HnswSearcher(_B200SearcherBase):
             local_prune = True
         elif pruning_strategy == "proportional":
             send_ratio = 1.0
-        if not self._sidecar("pq_pivots.bin").exists():
+        if not getattr(self, "_has_pq", False):
             # the reference ignores prune_ratio AND the strategy flags when no PQ files are loaded
             # (perform_pq_pruning needs hnsw.pq_data_loader, HNSW_search.cpp:442-445): the same call
             # succeeds on the stock backend, so it must not raise here

@@ -16,7 +16,7 @@ _lib = None
 
 EXPORTED_SYMBOLS = [
     "lb2_last_error", "lb2_version", "lb2_open", "lb2_close", "lb2_info", "lb2_set_vectors", "lb2_set_vectors_device",
-    "lb2_set_passages",
+    "lb2_set_passages", "lb2_load_pq_pruning",
     "lb2_encoder_weight_count", "lb2_set_encoder", "lb2_default_params", "lb2_search", "lb2_search_device",
     "lb2_last_query_stats", "lb2_encode_ids", "lb2_encode_tokens", "lb2_encode_range_device", "lb2_configure",
     "lb2_set_option",
@@ -94,6 +94,7 @@ def load():
     lib.lb2_set_vectors.argtypes = [C.c_void_p, C.c_void_p]
     lib.lb2_set_vectors_device.argtypes = [C.c_void_p, C.c_void_p]
     lib.lb2_set_passages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lb2_load_pq_pruning.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
     lib.lb2_encoder_weight_count.restype = C.c_size_t
     lib.lb2_encoder_weight_count.argtypes = [C.POINTER(EncoderConfig)]
     lib.lb2_set_encoder.argtypes = [C.c_void_p, C.POINTER(EncoderConfig), C.c_void_p, C.c_size_t]
@@ -128,7 +129,7 @@ def load():
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.lb2_build_workspace_bytes.restype = C.c_size_t
     lib.lb2_build_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
-    lib.lb2_build_select.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+    lib.lb2_build_select.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
@@ -202,6 +203,10 @@ class Index:
         if int(offsets[-1]) != tokens.size:
             raise ValueError("offsets[-1] must equal the token count")
         _check(self._lib.lb2_set_passages(self._h, _np_ptr(tokens), _np_ptr(offsets)), "lb2_set_passages")
+
+    def load_pq_pruning(self, pq_pivots_path: str, pq_compressed_path: str):
+        _check(self._lib.lb2_load_pq_pruning(self._h, str(pq_pivots_path).encode(), str(pq_compressed_path).encode()),
+               "lb2_load_pq_pruning")
 
     def set_encoder(self, cfg: EncoderConfig, weights: np.ndarray):
         weights = np.ascontiguousarray(weights, np.float32)
@@ -327,6 +332,6 @@ def build_insert_search(d_x_f16: int, n: int, d: int, metric_ip: bool, d_adj0: i
 
 
 def build_select(d_pd: int, pd_is_f32: bool, d_dn: int, d_cand: int, b: int, K: int, keep: int, d_out_ids: int,
-                 d_out_dist: int) -> None:
+                 d_out_dist: int, fill: int = 0) -> None:
     _check(load().lb2_build_select(C.c_void_p(d_pd), int(bool(pd_is_f32)), C.c_void_p(d_dn), C.c_void_p(d_cand), int(b), int(K),
-                                   int(keep), C.c_void_p(d_out_ids), C.c_void_p(d_out_dist)), "lb2_build_select")
+                                   int(keep), int(fill), C.c_void_p(d_out_ids), C.c_void_p(d_out_dist)), "lb2_build_select")

@@ -130,6 +130,11 @@ struct lb2_index {
     uint64_t* d_tok_off = nullptr;
     std::vector<uint64_t> h_tok_off;
     int max_token = 0;  // largest token id of the attached store (checked against the encoder's vocabulary)
+    // PQ-guided pruning data (lb2_load_pq_pruning)
+    PqDev pq;
+    float* dpq_tables_tr = nullptr; float* dpq_centroid = nullptr; uint32_t* dpq_chunk_offsets = nullptr; uint8_t* dpq_codes = nullptr;
+    int pq_cap = 16384;        // PQ candidates a query may accumulate (global / proportional strategies)
+    int alloc_pq_S = 0, alloc_pq_cap = 0, alloc_pq_chunks = 0, alloc_pq_dims = 0;
     Encoder enc;
     // tunables
     int cfg_slots = 0;
@@ -205,6 +210,9 @@ void free_state(lb2_index* x) {
     dev_free(&s.res_ids); dev_free(&s.res_dis); dev_free(&s.req_ids); dev_free(&s.visited);
     dev_free(&s.next_query); dev_free(&s.n_done); dev_free(&s.stamp); dev_free(&s.slot_of[0]); dev_free(&s.slot_of[1]);
     dev_free(&s.claim); dev_free(&s.uniq_node); dev_free(&s.seq_start);
+    dev_free(&s.pq_lut); dev_free(&s.pq_qprep); dev_free(&s.pq_qd); dev_free(&s.pq_qid); dev_free(&s.pq_qn); dev_free(&s.pq_qhead);
+    dev_free(&s.error);
+    x->alloc_pq_S = 0;
     dev_free(&x->d_E);
     if (x->h_ctrl) cudaFreeHost(x->h_ctrl);
     if (x->h_bounds) cudaFreeHost(x->h_bounds);
@@ -218,8 +226,10 @@ bool ensure_state(lb2_index* x, int S, const TravParams& p, bool recompute) {
     const TravParams& a = x->alloc_p;
     const int64_t need_rows = !recompute ? 0 : (x->dedup_call_scope ? std::max<int64_t>(x->g.ntotal, (int64_t)S * p.cap_req) : (int64_t)S * p.cap_req);
     // strides depend on S / hcap / k / cap_req: reallocate on any change (calls with stable params reuse)
+    const bool pq_ok = !p.pq_mode || (x->alloc_pq_S == S && x->alloc_pq_cap == x->pq_cap && x->alloc_pq_chunks == x->pq.n_chunks &&
+                                      x->alloc_pq_dims == x->pq.ndims);
     if (x->alloc_S == S && a.hcap == p.hcap && a.k == p.k && a.cap_req == p.cap_req && (!recompute || x->alloc_recompute) &&
-        x->cap_E_rows >= need_rows)
+        x->cap_E_rows >= need_rows && pq_ok)
         return true;
     free_state(x);
     TravState& s = x->st;
@@ -236,7 +246,15 @@ bool ensure_state(lb2_index* x, int S, const TravParams& p, bool recompute) {
               dev_alloc(&s.res_ids, Ss * p.k) && dev_alloc(&s.res_dis, Ss * p.k) &&
               dev_alloc(&s.req_ids, Ss * p.cap_req) && dev_alloc(&s.visited, Ss * (size_t)s.vis_words) &&
               dev_alloc(&s.next_query, 1) && dev_alloc(&s.n_done, 1);
+    ok = ok && dev_alloc(&s.error, 1);
+    if (ok && p.pq_mode) {
+        ok = dev_alloc(&s.pq_lut, Ss * (size_t)x->pq.n_chunks * 256) && dev_alloc(&s.pq_qprep, Ss * (size_t)x->pq.ndims) &&
+             dev_alloc(&s.pq_qd, Ss * (size_t)x->pq_cap) && dev_alloc(&s.pq_qid, Ss * (size_t)x->pq_cap) &&
+             dev_alloc(&s.pq_qn, Ss) && dev_alloc(&s.pq_qhead, Ss);
+        if (ok) { x->alloc_pq_S = S; x->alloc_pq_cap = x->pq_cap; x->alloc_pq_chunks = x->pq.n_chunks; x->alloc_pq_dims = x->pq.ndims; }
+    }
     if (!ok) { free_state(x); return false; }
+    s.pq_cap = x->pq_cap;
     if (cudaMemsetAsync(s.visited, 0, Ss * (size_t)s.vis_words * 4, x->stream) != cudaSuccess) {
         set_error("memset(visited) failed");
         free_state(x);
@@ -286,10 +304,7 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     if (x->is_vamana) { set_error("this handle is a DiskANN index: use lb2_diskann_search"); return LB2_ERR_STATE; }
     if (nq < 0 || k <= 0 || k > 4096) { set_error("bad nq/k (nq=%lld k=%lld)", (long long)nq, (long long)k); return LB2_ERR_ARG; }
     if (P.efSearch <= 0 || P.efSearch > 16384) { set_error("efSearch out of range: %d", P.efSearch); return LB2_ERR_ARG; }
-    if (P.pq_pruning_ratio != 0.f || P.local_prune || P.send_neigh_times_ratio != 0.f) {
-        set_error("PQ-guided pruning (prune_ratio / pruning_strategy) is not implemented in this backend");
-        return LB2_ERR_UNSUPPORTED;
-    }
+    if (P.pq_pruning_ratio < 0.f || P.pq_pruning_ratio > 1.f) { set_error("pq_pruning_ratio must lie in [0, 1]"); return LB2_ERR_ARG; }
     const bool recompute = P.recompute != 0;
     if (recompute && (!x->d_tokens || !x->enc.loaded)) {
         set_error("recompute search needs lb2_set_passages() and lb2_set_encoder() first");
@@ -328,8 +343,16 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     tp.batch_size = std::max(0, P.batch_size);
     tp.check_rel = P.check_relative_distance != 0;
     const int deg0 = std::max(1, x->g.maxdeg0);
-    tp.cap_req = std::max(std::max(1, x->g.maxdeg_up), tp.batch_size > 0 ? tp.batch_size + deg0 : tp.beam * deg0);
-    tp.p2 = next_pow2(tp.cap_req);
+    tp.cap_new = std::max(std::max(1, x->g.maxdeg_up), tp.batch_size > 0 ? tp.batch_size + deg0 : tp.beam * deg0);
+    tp.p2 = next_pow2(tp.cap_new);
+    // PQ-guided pruning: like the reference, only when PQ data was loaded AND the parameters ask for it
+    // (perform_pq_pruning, HNSW_search.cpp:442-445); otherwise the three knobs are ignored
+    tp.pq_ratio = 1.0f - P.pq_pruning_ratio;
+    tp.pq_mode = 0;
+    if (x->dpq_codes && (tp.pq_ratio < 1.f || P.local_prune || P.send_neigh_times_ratio != 0.f))
+        tp.pq_mode = P.local_prune ? 2 : (P.send_neigh_times_ratio > 1e-6f ? 3 : 1);
+    // a hop selects at most (new neighbours) + (growth of the examined share of the queue) + 1 nodes: <= 2 cap_new + 2
+    tp.cap_req = tp.pq_mode ? 2 * tp.cap_new + 2 : tp.cap_new;
 
     int S;
     if (x->cfg_slots > 0) S = x->cfg_slots;
@@ -346,6 +369,8 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     s.queries = d_q; s.nq = nq; s.outD = d_D; s.outI = d_I; s.out_ndis = x->d_qndis; s.out_nhops = x->d_qnhops;
     s.recompute = recompute ? 1 : 0;
     s.vectors = x->d_vectors; s.E = x->d_E; s.tok_off = x->d_tok_off; s.max_pos = x->enc.cfg.max_pos;
+    s.pq = x->pq;
+    cudaMemsetAsync(s.error, 0, sizeof(int), st);
 
     x->ev_total.total_ms = 0; x->ev_enc.total_ms = 0;
     for (auto& pl : g_prof_pool) pl.total_ms = 0;
@@ -411,6 +436,12 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     cudaError_t e = cudaStreamSynchronize(st);
     g_prof_on = false;
     if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
+    int kerr = 0;
+    cudaMemcpy(&kerr, s.error, sizeof(int), cudaMemcpyDeviceToHost);
+    if (kerr) {
+        set_error("PQ-guided pruning: a query exceeded %d PQ candidates (raise it with lb2_set_option(\"pq_queue_cap\"))", x->pq_cap);
+        return LB2_ERR_STATE;
+    }
     int done = 0;
     cudaMemcpy(&done, s.n_done, sizeof(int), cudaMemcpyDeviceToHost);
     if (done != nq) { set_error("internal: %d of %lld queries finished", done, (long long)nq); return LB2_ERR_CUDA; }
@@ -772,6 +803,7 @@ void lb2_close(lb2_index* x) {
     encoder_free(&x->enc);
     dev_free(&x->d_node_offsets); dev_free(&x->d_level_ptr); dev_free(&x->d_nbrs);
     dev_free(&x->d_vectors); dev_free(&x->d_tokens); dev_free(&x->d_tok_off);
+    dev_free(&x->dpq_tables_tr); dev_free(&x->dpq_centroid); dev_free(&x->dpq_chunk_offsets); dev_free(&x->dpq_codes);
     dev_free(&x->d_q); dev_free(&x->d_D); dev_free(&x->d_I); dev_free(&x->d_qndis); dev_free(&x->d_qnhops);
     dev_free(&x->d_enc_node); dev_free(&x->d_enc_start); dev_free(&x->d_enc_out);
     free_vamana(x);
@@ -834,6 +866,29 @@ int lb2_set_passages(lb2_index* x, const uint16_t* tokens, const uint64_t* offse
     return LB2_OK;
 }
 
+int lb2_load_pq_pruning(lb2_index* x, const char* pq_pivots_path, const char* pq_compressed_path) {
+    if (!x || !pq_pivots_path || !pq_compressed_path) { set_error("null argument"); return LB2_ERR_ARG; }
+    if (x->is_vamana) { set_error("this handle is a DiskANN index"); return LB2_ERR_STATE; }
+    PqHost h;
+    std::string err;
+    try {
+        if (!read_pq_files(pq_pivots_path, pq_compressed_path, &h, &err)) { set_error("%s", err.c_str()); return LB2_ERR_IO; }
+    } catch (const std::exception& e) {
+        set_error("%s: malformed PQ file (%s)", pq_pivots_path, e.what());
+        return LB2_ERR_IO;
+    }
+    if (h.n != x->g.ntotal) { set_error("PQ codes cover %lld vectors, the index has %lld", (long long)h.n, (long long)x->g.ntotal); return LB2_ERR_ARG; }
+    // the reference copies ndims - 1 query coordinates and appends a zero (HNSW_search.cpp:451-456)
+    if (h.ndims < 2 || h.ndims - 1 > x->g.d) { set_error("PQ dimension %d does not fit queries of dimension %d", h.ndims, x->g.d); return LB2_ERR_ARG; }
+    if (!use_device(x)) return LB2_ERR_CUDA;
+    if (!upload(&x->dpq_tables_tr, h.tables_tr) || !upload(&x->dpq_centroid, h.centroid) || !upload(&x->dpq_chunk_offsets, h.chunk_offsets) ||
+        !upload(&x->dpq_codes, h.codes))
+        return LB2_ERR_CUDA;
+    x->pq.tables_tr = x->dpq_tables_tr; x->pq.centroid = x->dpq_centroid; x->pq.chunk_offsets = x->dpq_chunk_offsets;
+    x->pq.codes = x->dpq_codes; x->pq.ndims = h.ndims; x->pq.n_chunks = h.n_chunks;
+    return LB2_OK;
+}
+
 size_t lb2_encoder_weight_count(const lb2_encoder_config* c) {
     if (!c) return 0;
     EncoderConfig e{c->vocab_size, c->hidden, c->layers, c->heads, c->ffn, c->max_pos, c->type_vocab, c->ln_eps, c->pooling, c->normalize};
@@ -875,6 +930,11 @@ int lb2_set_option(lb2_index* x, const char* key, int64_t value) {
         return LB2_OK;
     }
     if (!strcmp(key, "profile")) { x->profile_gemm = value != 0; return LB2_OK; }
+    if (!strcmp(key, "pq_queue_cap")) {
+        if (value < 256 || value > (1 << 22)) { set_error("pq_queue_cap must lie in [256, 4194304]"); return LB2_ERR_ARG; }
+        x->pq_cap = (int)value;
+        return LB2_OK;
+    }
     set_error("unknown option '%s'", key);
     return LB2_ERR_ARG;
 }

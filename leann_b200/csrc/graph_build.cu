@@ -254,11 +254,13 @@ build_insert_search_kernel(const BuildArgs a) {
 
 // HNSW::shrink_neighbor_list over a sorted candidate row (closest first; invalid entries = -1 at the end).
 //   pd [b, K, K]  pairwise candidate distances (fp16 or fp32),  dn [b, K] distance of the node to each candidate.
-// Keeps candidate j iff no already kept i has pd[j][i] < dn[j]; stops at `keep`.  Output ids/dist [b, keep], -1 / FLT_MAX padded.
+// Keeps candidate j iff no already kept i has pd[j][i] < dn[j]; stops at `keep`.  fill > 0: a list that ends with fewer than
+// `fill` links is topped up with the nearest rejected candidates ("outsiders", the keep_max_size_level0 branch of the
+// reference, :459-467, with a settable floor instead of max_size).  Output ids/dist [b, keep], -1 / FLT_MAX padded.
 template <typename PT>
 __global__ void __launch_bounds__(128)
 build_select_kernel(const PT* __restrict__ pd, const float* __restrict__ dn, const int* __restrict__ cand, long long b, int K,
-                    int keep, int* __restrict__ out_ids, float* __restrict__ out_dist) {
+                    int keep, int fill, int* __restrict__ out_ids, float* __restrict__ out_dist) {
     __shared__ int s_kept[4][MAX_NEW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 4 + warp;
@@ -279,6 +281,22 @@ build_select_kernel(const PT* __restrict__ pd, const float* __restrict__ dn, con
                 kept[nk] = j;
                 out_ids[row * keep + nk] = id;
                 out_dist[row * keep + nk] = dj;
+            }
+            nk++;
+        }
+        __syncwarp();
+    }
+    if (nk < fill) {  // outsiders, nearest first; kept[] is ascending, so one merge-like scan finds the rejected ones
+        const int nk0 = nk;
+        int ki = 0;
+        for (int j = 0; j < K && nk < fill; j++) {
+            const int id = cr[j];
+            if (id < 0) break;
+            while (ki < nk0 && kept[ki] < j) ki++;
+            if (ki < nk0 && kept[ki] == j) continue;
+            if (lane == 0) {
+                out_ids[row * keep + nk] = id;
+                out_dist[row * keep + nk] = dr[j];
             }
             nk++;
         }
@@ -358,17 +376,18 @@ size_t lb2_build_workspace_bytes(int32_t ef, int32_t cap0) {
 }
 
 int lb2_build_select(const void* d_pd, int32_t pd_is_f32, const float* d_dn, const int32_t* d_cand, int64_t b, int32_t K,
-                     int32_t keep, int32_t* d_out_ids, float* d_out_dist) {
-    if (!d_pd || !d_dn || !d_cand || !d_out_ids || !d_out_dist || b < 0 || K < 1 || keep < 1 || keep > MAX_NEW) {
+                     int32_t keep, int32_t fill, int32_t* d_out_ids, float* d_out_dist) {
+    if (!d_pd || !d_dn || !d_cand || !d_out_ids || !d_out_dist || b < 0 || K < 1 || keep < 1 || keep > MAX_NEW || fill < 0 ||
+        fill > keep) {
         set_error("lb2_build_select: bad arguments (keep <= %d)", MAX_NEW);
         return LB2_ERR_ARG;
     }
     if (b == 0) return LB2_OK;
     const unsigned grid = static_cast<unsigned>((b + 3) / 4);
     if (pd_is_f32)
-        build_select_kernel<float><<<grid, 128>>>(static_cast<const float*>(d_pd), d_dn, d_cand, b, K, keep, d_out_ids, d_out_dist);
+        build_select_kernel<float><<<grid, 128>>>(static_cast<const float*>(d_pd), d_dn, d_cand, b, K, keep, fill, d_out_ids, d_out_dist);
     else
-        build_select_kernel<__half><<<grid, 128>>>(static_cast<const __half*>(d_pd), d_dn, d_cand, b, K, keep, d_out_ids, d_out_dist);
+        build_select_kernel<__half><<<grid, 128>>>(static_cast<const __half*>(d_pd), d_dn, d_cand, b, K, keep, fill, d_out_ids, d_out_dist);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("build_select_kernel launch failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     return LB2_OK;

@@ -77,7 +77,9 @@ struct Warp {
     float* q;
     int* h_ids; float* h_dis;
     float* r_dis; int* r_ids;
-    int* rq; float* rq_dis;
+    int* rq; float* rq_dis;  // rq: the hop's gathered neighbours (sort buffer, p2); rq_dis: distances of the requests
+    int* req;                // the hop's distance requests, in the order they are folded (== rq without PQ pruning)
+    float* pqd;              // PQ distances of the gathered neighbours (p2; PQ pruning only)
 };
 
 // MinimaxHeap::push (HNSW.cpp:1263-1274); lane 0 only
@@ -190,6 +192,127 @@ __device__ int warp_unique(int* a, int n, int lane) {
     return out;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// PQ-guided pruning (faiss/impl/HNSW_search.cpp:442-465, 645-750; arithmetic of faiss/impl/pq.cpp in its own operation
+// order: double-precision differences, float accumulation — bit-identical tables and PQ distances).
+
+// query -> (append 0, normalise, centre) -> per-chunk distance table.  HNSW_search.cpp:447-460, pq.cpp:140-190
+__device__ void pq_build_lut(const PqDev& pq, const float* q_s, int d, float* qprep, float* lut, int lane) {
+    const int dim = pq.ndims;
+    for (int i = lane; i < dim; i += 32) qprep[i] = (i < dim - 1 && i < d) ? q_s[i] : 0.f;
+    __syncwarp();
+    float fn = 1.f;
+    if (lane == 0) {
+        double norm_sq = 0.0;
+        for (int i = 0; i < dim; i++) norm_sq = __dadd_rn(norm_sq, __dmul_rn((double)qprep[i], (double)qprep[i]));
+        double norm = __dsqrt_rn(norm_sq);
+        if (norm <= 0.0) norm = 1.0;
+        fn = __double2float_rn(norm);
+    }
+    fn = __shfl_sync(0xffffffffu, fn, 0);
+    for (int i = lane; i < dim; i += 32) qprep[i] = __fsub_rn(__fdiv_rn(qprep[i], fn), pq.centroid[i]);
+    __syncwarp();
+    for (int c = 0; c < pq.n_chunks; c++) {
+        const uint32_t j0 = pq.chunk_offsets[c], j1 = pq.chunk_offsets[c + 1];
+        for (int idx = lane; idx < 256; idx += 32) {
+            float acc = 0.f;
+            for (uint32_t j = j0; j < j1; j++) {
+                const double diff = __dsub_rn((double)pq.tables_tr[256 * (size_t)j + idx], (double)qprep[j]);
+                acc = __fadd_rn(acc, __double2float_rn(__dmul_rn(diff, diff)));
+            }
+            lut[256 * c + idx] = acc;
+        }
+    }
+    __syncwarp();
+}
+
+// pq_distance_lookup (pq.cpp:207-224): chunk-major float accumulation from 0
+__device__ __forceinline__ float pq_lookup(const PqDev& pq, const float* lut, int id) {
+    const uint8_t* code = pq.codes + (size_t)id * pq.n_chunks;
+    float acc = 0.f;
+    for (int c = 0; c < pq.n_chunks; c++) acc = __fadd_rn(acc, __ldcg(lut + 256 * c + code[c]));
+    return acc;
+}
+
+__device__ __forceinline__ bool pair_lt(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
+
+// ascending bitonic sort of the pairs (kd[i], ki[i]), i < P (power of two), by (distance, id): std::pair ordering
+__device__ void warp_sort_pairs(float* kd, int* ki, int P, int lane) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P; i += 32) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float d1 = kd[i], d2 = kd[ixj];
+                    const int i1 = ki[i], i2 = ki[ixj];
+                    const bool up = ((i & k) == 0);
+                    if (pair_lt(d2, i2, d1, i1) == up) { kd[i] = d2; ki[i] = i2; kd[ixj] = d1; ki[ixj] = i1; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// number of entries of the ascending array (ad, ai)[lo, hi) that are <  (d, id)   [strict]   /   <= (d, id)   [!strict]
+__device__ __forceinline__ int pairs_rank(const float* ad, const int* ai, int lo, int hi, float d, int id, bool strict) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float md = ad[mid];
+        const int mi = ai[mid];
+        const bool go_right = strict ? pair_lt(md, mi, d, id) : !pair_lt(d, id, md, mi);
+        if (go_right) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Merge the hop's sorted batch (bd, bi)[0, nb) (shared memory) into the slot's ascending candidate array (qd, qi)[head, qn)
+// (global memory).  unique: drop batch entries already present (std::set semantics of the proportional mode).
+// `pos` is nb ints of scratch in shared memory.  Returns the new qn, or -1 on overflow.
+__device__ int pq_merge(float* qd, int* qi, int head, int qn, int cap, float* bd, int* bi, int nb, bool unique, int* pos, int lane) {
+    // rank of every batch entry among the old entries, and (set mode) whether it is already there
+    int kept = 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int j = b0 + lane;
+        int r = 0;
+        bool keep = false;
+        if (j < nb) {
+            r = pairs_rank(qd, qi, head, qn, bd[j], bi[j], true);          // old entries strictly smaller
+            keep = !(unique && r < qn && qd[r] == bd[j] && qi[r] == bi[j]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int o = kept + __popc(m & ((1u << lane) - 1));
+            pos[o] = r;                                                     // compacted: rank in the OLD array
+            const float dd = bd[j]; const int ii = bi[j];
+            __syncwarp(m);
+            bd[o] = dd; bi[o] = ii;                                         // o <= j: in-place compaction is safe chunk by chunk
+        }
+        kept += __popc(m);
+        __syncwarp();
+    }
+    nb = kept;
+    if (qn + nb > cap) return -1;
+    // move the old entries up, highest chunk first: entry i goes to i + (number of kept batch entries ranked <= i)
+    for (int hi = qn; hi > head; hi -= 32) {
+        const int i = hi - 1 - lane;
+        float dd = 0.f; int ii = 0; int shift = 0;
+        if (i >= head) {
+            dd = qd[i]; ii = qi[i];
+            int lo2 = 0, hi2 = nb;   // batch entries whose rank (insertion point in the old array) is <= i
+            while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (pos[mid] <= i) lo2 = mid + 1; else hi2 = mid; }
+            shift = lo2;
+        }
+        __syncwarp();
+        if (i >= head && shift) { qd[i + shift] = dd; qi[i + shift] = ii; }
+        __syncwarp();
+    }
+    for (int j = lane; j < nb; j += 32) { qd[pos[j] + j] = bd[j]; qi[pos[j] + j] = bi[j]; }
+    __syncwarp();
+    return qn + nb;
+}
+
 __global__ void __launch_bounds__(STEP_WARPS * 32)
 hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int max_iters) {
     extern __shared__ __align__(16) uint8_t step_smem[];
@@ -201,7 +324,8 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
 
     const int d = g.d;
     const int dpad = (d + 3) & ~3;
-    const size_t per_warp = (size_t)dpad * 4 + (size_t)p.hcap * 8 + (size_t)p.k * 8 + (size_t)p.p2 * 4 + (size_t)p.cap_req * 4;
+    const size_t per_warp = (size_t)dpad * 4 + (size_t)p.hcap * 8 + (size_t)p.k * 8 + (size_t)p.p2 * 4 + (size_t)p.cap_req * 4 +
+                            (p.pq_mode ? (size_t)p.cap_req * 4 + (size_t)p.p2 * 4 : 0);
     uint8_t* base = step_smem + ((per_warp + 15) & ~size_t(15)) * warp;
     Warp w;
     w.q = reinterpret_cast<float*>(base);
@@ -211,6 +335,8 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
     w.r_ids = reinterpret_cast<int*>(w.r_dis + p.k);
     w.rq = w.r_ids + p.k;
     w.rq_dis = reinterpret_cast<float*>(w.rq + p.p2);
+    w.req = p.pq_mode ? reinterpret_cast<int*>(w.rq_dis + p.cap_req) : w.rq;
+    w.pqd = p.pq_mode ? reinterpret_cast<float*>(w.req + p.cap_req) : nullptr;
 
     // ---- load slot state
     int qid = st.qid[slot], level = st.level[slot], nearest = st.nearest[slot], prev_nearest = st.prev_nearest[slot];
@@ -227,7 +353,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
     if (phase != PH_FETCH) {
         for (int i = lane; i < hk; i += 32) { w.h_ids[i] = g_hids[i]; w.h_dis[i] = g_hdis[i]; }
         for (int i = lane; i < p.k; i += 32) { w.r_ids[i] = g_rids[i]; w.r_dis[i] = g_rdis[i]; }
-        for (int i = lane; i < n_req; i += 32) w.rq[i] = g_req[i];
+        for (int i = lane; i < n_req; i += 32) w.req[i] = g_req[i];
         const float* qg = st.queries + (size_t)qid * d;
         for (int j = lane; j < d; j += 32) w.q[j] = qg[j];
     }
@@ -243,7 +369,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
         // =========================== score + fold the pending requests ===========================
         if (have_pending) {
             for (int i = 0; i < n_req; i++) {
-                const int node = w.rq[i];
+                const int node = w.req[i];
                 const float* e = st.recompute ? st.E + (size_t)slot_rd[node] * d : st.vectors + (size_t)node * d;
                 const float dist = canon_dist(w.q, e, d, g.metric_ip, lane);
                 if (lane == 0) w.rq_dis[i] = dist;
@@ -257,7 +383,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
             } else if (phase == PH_GREEDY) {  // HNSW.cpp:1043-1061
                 for (int i = 0; i < n_req; i++) {
                     const float dd = w.rq_dis[i];
-                    if (dd < d_nearest) { d_nearest = dd; nearest = w.rq[i]; }
+                    if (dd < d_nearest) { d_nearest = dd; nearest = w.req[i]; }
                 }
                 ndis += n_req;
                 nhops++;
@@ -270,7 +396,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                     float thr = w.r_dis[0];
                     for (int i = 0; i < n_req; i++) {
                         const float dd = w.rq_dis[i];
-                        const int id = w.rq[i];
+                        const int id = w.req[i];
                         if (dd < thr) { heap_replace_top(p.k, w.r_dis, w.r_ids, dd, id); thr = w.r_dis[0]; }
                         mm_push(w, hk, hnvalid, p.hcap, id, dd);
                     }
@@ -300,7 +426,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                 hk = 0; hnvalid = 0; nstep = 0; ndis = 0; nhops = 0; pend_beam = 0;
                 __syncwarp();
                 phase = PH_ENTRY;
-                if (lane == 0) w.rq[0] = g.entry_point;
+                if (lane == 0) w.req[0] = g.entry_point;
                 n_req = 1;
                 __syncwarp();
                 break;
@@ -316,7 +442,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                     if (level < 1) phase = PH_BASE_INIT;
                     continue;
                 }
-                for (int i = lane; i < n; i += 32) w.rq[i] = g.nbrs[b + i];
+                for (int i = lane; i < n; i += 32) w.req[i] = g.nbrs[b + i];
                 n_req = n;
                 __syncwarp();
                 break;
@@ -331,6 +457,12 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                 hnvalid = __shfl_sync(0xffffffffu, hnvalid, 0);
                 nstep = 0;
                 __syncwarp();
+                if (p.pq_mode) {  // HNSW_search.cpp:447-460: the query's PQ table; fresh candidate queue / set
+                    pq_build_lut(st.pq, w.q, d, st.pq_qprep + (size_t)slot * st.pq.ndims,
+                                 st.pq_lut + (size_t)slot * st.pq.n_chunks * 256, lane);
+                    if (lane == 0) { st.pq_qn[slot] = 0; st.pq_qhead[slot] = 0; }
+                    __syncwarp();
+                }
                 phase = PH_BASE;
                 continue;
             }
@@ -404,7 +536,8 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                     cnt += __popc(m);
                 }
                 nbeam++;
-                total_neighbors = static_cast<int>(static_cast<float>(total_neighbors) + static_cast<float>(cnt));
+                total_neighbors = static_cast<int>(static_cast<float>(total_neighbors) +
+                                                   static_cast<float>(cnt) * (p.pq_mode ? p.pq_ratio : 1.0f));  // :567-568, :610-611
                 __syncwarp();
             }
             if (nbeam == 0) continue;  // HNSW_search.cpp:618-620
@@ -417,9 +550,66 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                 warp_sort(w.rq, P, lane);
                 nnew = warp_unique(w.rq, nnew, lane);
             }
-            for (int i = lane; i < nnew; i += 32) {
-                const int v1 = w.rq[i];
-                atomicOr(&vis[v1 >> 5], 1u << (v1 & 31));
+            if (p.pq_mode) {
+                // ---- :645-750: PQ distances of the hop's unvisited neighbours, then one of three selections; only the
+                // selected nodes are marked visited and scored exactly, in the order they are selected
+                const float* lut = st.pq_lut + (size_t)slot * st.pq.n_chunks * 256;
+                for (int i = lane; i < P; i += 32) w.pqd[i] = (i < nnew) ? pq_lookup(st.pq, lut, w.rq[i]) : FLT_MAX;
+                __syncwarp();
+                if (nnew > 1) warp_sort_pairs(w.pqd, w.rq, P, lane);
+                int ns = 0;
+                if (p.pq_mode == 2) {  // local: the closest pq_select_ratio share of this hop's neighbours (:683-707)
+                    const size_t num = static_cast<size_t>(p.pq_ratio * static_cast<float>(static_cast<size_t>(nnew)));
+                    ns = num < static_cast<size_t>(nnew) ? static_cast<int>(num) : nnew;
+                    for (int i = lane; i < ns; i += 32) w.req[i] = w.rq[i];
+                } else {
+                    float* qd = st.pq_qd + (size_t)slot * st.pq_cap;
+                    int* qi = st.pq_qid + (size_t)slot * st.pq_cap;
+                    int head = st.pq_qhead[slot], qn = st.pq_qn[slot];
+                    const int merged = pq_merge(qd, qi, head, qn, st.pq_cap, w.pqd, w.rq, nnew, p.pq_mode == 3, w.req, lane);
+                    if (merged < 0) { if (lane == 0) atomicExch(st.error, 1); } else qn = merged;
+                    if (p.pq_mode == 3) {  // proportional: std::set, the max(1, n_new * ratio) smallest, erased (:714-731)
+                        int num = static_cast<int>(static_cast<float>(static_cast<size_t>(nnew)) * p.pq_ratio);
+                        if (num < 1) num = 1;
+                        ns = (qn - head) < num ? (qn - head) : num;
+                        for (int i = lane; i < ns; i += 32) w.req[i] = qi[head + i];
+                        head += ns;
+                    } else {  // global: look at the max(1, size * ratio) smallest of everything seen, skip the visited (:732-750)
+                        int num = static_cast<int>(static_cast<float>(static_cast<size_t>(qn)) * p.pq_ratio);
+                        if (num < 1) num = 1;
+                        if (num > qn) num = qn;
+                        for (int b0 = 0; b0 < num; b0 += 32) {
+                            const int i = b0 + lane;
+                            bool take = false;
+                            int id = -1;
+                            if (i < num) {
+                                id = qi[i];
+                                const bool dup = i > 0 && qi[i - 1] == id;  // a re-pushed node sits next to its first copy
+                                take = !dup && (((__ldcg(&vis[id >> 5]) >> (id & 31)) & 1u) == 0);
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, take);
+                            if (take) {
+                                const int o = ns + __popc(m & ((1u << lane) - 1));
+                                if (o < p.cap_req) w.req[o] = id;
+                            }
+                            ns += __popc(m);
+                        }
+                        if (ns > p.cap_req) { if (lane == 0) atomicExch(st.error, 2); ns = p.cap_req; }
+                    }
+                    __syncwarp();
+                    if (lane == 0) { st.pq_qn[slot] = qn; st.pq_qhead[slot] = head; }
+                }
+                __syncwarp();
+                for (int i = lane; i < ns; i += 32) {
+                    const int v1 = w.req[i];
+                    atomicOr(&vis[v1 >> 5], 1u << (v1 & 31));
+                }
+                nnew = ns;
+            } else {
+                for (int i = lane; i < nnew; i += 32) {
+                    const int v1 = w.rq[i];
+                    atomicOr(&vis[v1 >> 5], 1u << (v1 & 31));
+                }
             }
             __syncwarp();
             if (nnew == 0) {  // distances_batch on an empty set; :781-787
@@ -436,7 +626,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
         if (st.recompute) {
             // claim a row of the hop's unique work list for every node nobody requested yet this hop
             for (int i = lane; i < n_req; i += 32) {
-                const int node = w.rq[i];
+                const int node = w.req[i];
                 const uint32_t old = atomicMax(&st.stamp[node], st.stamp_value);
                 if (old < st.stamp_value) {
                     int len = static_cast<int>(st.tok_off[node + 1] - st.tok_off[node]);
@@ -465,7 +655,7 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
     if (phase != PH_IDLE) {
         for (int i = lane; i < hk; i += 32) { g_hids[i] = w.h_ids[i]; g_hdis[i] = w.h_dis[i]; }
         for (int i = lane; i < p.k; i += 32) { g_rids[i] = w.r_ids[i]; g_rdis[i] = w.r_dis[i]; }
-        for (int i = lane; i < n_req; i += 32) g_req[i] = w.rq[i];
+        for (int i = lane; i < n_req; i += 32) g_req[i] = w.req[i];
     }
 }
 
@@ -484,7 +674,8 @@ __global__ void init_slots_kernel(TravState st) {
 
 size_t step_smem_bytes(const TravParams& p, int d, int warps) {
     const int dpad = (d + 3) & ~3;
-    const size_t per_warp = (size_t)dpad * 4 + (size_t)p.hcap * 8 + (size_t)p.k * 8 + (size_t)p.p2 * 4 + (size_t)p.cap_req * 4;
+    const size_t per_warp = (size_t)dpad * 4 + (size_t)p.hcap * 8 + (size_t)p.k * 8 + (size_t)p.p2 * 4 + (size_t)p.cap_req * 4 +
+                            (p.pq_mode ? (size_t)p.cap_req * 4 + (size_t)p.p2 * 4 : 0);
     return ((per_warp + 15) & ~size_t(15)) * warps;
 }
 

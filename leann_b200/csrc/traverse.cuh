@@ -30,7 +30,20 @@ struct TravParams {
     int batch_size; // batch_size (0 = disabled)
     int check_rel;  // check_relative_distance
     int cap_req;    // max ids one hop can request
-    int p2;         // next power of two >= cap_req (sort buffer)
+    int p2;         // next power of two >= cap_new (sort buffer)
+    int cap_new;    // max unvisited neighbours one hop can gather (= cap_req without PQ pruning)
+    // PQ-guided pruning (faiss/impl/HNSW_search.cpp:442-465, 645-750): 0 off, 1 global queue, 2 local, 3 proportional
+    int pq_mode;
+    float pq_ratio; // pq_select_ratio = 1 - pq_pruning_ratio
+};
+
+// PQ pruning data: PQPrunerDataLoader (faiss/impl/pq.h:12-43) + HNSW::pq_codes (HNSW_search.cpp:253-297), device copies
+struct PqDev {
+    const float* tables_tr = nullptr;        // [ndims, 256]
+    const float* centroid = nullptr;         // [ndims]
+    const uint32_t* chunk_offsets = nullptr; // [n_chunks + 1]
+    const uint8_t* codes = nullptr;          // [ntotal, n_chunks]
+    int ndims = 0, n_chunks = 0;
 };
 
 // Per-slot traversal state (one slot = one in-flight query, owned by one warp) + batch plumbing.
@@ -71,6 +84,15 @@ struct TravState {
     int call_scope;
     uint32_t stamp_value;       // value written to stamp[]: hop epoch (hop scope) or call epoch (call scope)
     int row_base_hop;           // first E row of this hop's new nodes (0 in hop scope)
+    // PQ pruning state (allocated only when a search asks for pruning)
+    PqDev pq;
+    float* pq_lut;              // [S, n_chunks * 256] per-query distance tables
+    float* pq_qprep;            // [S, ndims] preprocessed query (scratch of the table build)
+    float* pq_qd; int* pq_qid;  // [S, pq_cap] the query's PQ candidates, ascending (distance, id): the content of the
+                                //   reference's pq_candidate_queue (global mode) / pq_candidate_set (proportional mode)
+    int* pq_qn; int* pq_qhead;  // [S] valid range [head, n)
+    int pq_cap;
+    int* error;                 // != 0: a slot overflowed its PQ candidate array
 };
 
 size_t step_smem_bytes(const TravParams& p, int d, int warps);

@@ -50,17 +50,9 @@ struct File {
 
 }  // namespace
 
-bool read_diskann_index(const char* index_prefix, const char* partition_prefix, int metric, VamanaHost* o, std::string* err) {
-    const std::string p = index_prefix ? index_prefix : "";
-    const std::string pp = partition_prefix ? partition_prefix : "";
-    if (p.empty()) { *err = "index_prefix is empty"; return false; }
-    if (metric < 0 || metric > 2) { *err = "metric must be 0 (l2), 1 (mips) or 2 (cosine)"; return false; }
-    o->metric = metric;
-    o->partitioned = !pp.empty();
-    const std::string pivots = p + "_pq_pivots.bin", compressed = p + "_pq_compressed.bin", disk = p + "_disk.index";
-    if (exists(pivots + "_rotation_matrix.bin")) { *err = "OPQ rotation matrix is not supported"; return false; }
-    if (!o->partitioned && exists(disk + "_pq_pivots.bin")) { *err = "disk-PQ indexes are not supported"; return false; }
-    if (exists(disk + "_labels.txt")) { *err = "filtered (labelled) indexes are not supported"; return false; }
+// <p>_pq_compressed.bin + <p>_pq_pivots.bin (also what HNSW::load_pq_pruning_data reads for PQ-guided pruning,
+// leann-backend-hnsw/third_party/faiss/faiss/impl/HNSW_search.cpp:253-297, impl/pq.cpp:41-138)
+bool read_pq_files(const std::string& pivots, const std::string& compressed, PqHost* o, std::string* err) {
     int64_t r = 0, c = 0;
     {   // ---- PQ codes
         File f(compressed, err);
@@ -78,17 +70,38 @@ bool read_diskann_index(const char* index_prefix, const char* partition_prefix, 
         std::vector<float> tables;
         if (!f.bin<float>(offs[0], &tables, &r, &c, 256ull * 65536)) return false;
         if (r != 256 || c <= 0) { *err = pivots + ": expected 256 pivots"; return false; }
-        o->data_dim = (int)c;
+        o->ndims = (int)c;
         if (!f.bin<float>(offs[1], &o->centroid, &r, &c, 65536)) return false;
-        if (r != o->data_dim || c != 1) { *err = pivots + ": centroid shape mismatch"; return false; }
+        if (r != o->ndims || c != 1) { *err = pivots + ": centroid shape mismatch"; return false; }
         const bool old_type = offs.size() == 5;  // 5-offset files keep the chunk offsets in slot 3 (src/pq.cpp:126-131)
         if (!f.bin<uint32_t>(offs[old_type ? 3 : 2], &o->chunk_offsets, &r, &c, 1024)) return false;
         if (c != 1 || r != o->n_chunks + 1) { *err = pivots + ": chunk offsets do not match the compressed file"; return false; }
         for (int i = 0; i < o->n_chunks; i++)
-            if (o->chunk_offsets[i] > o->chunk_offsets[i + 1] || o->chunk_offsets[i + 1] > (uint32_t)o->data_dim) { *err = pivots + ": chunk offsets out of range"; return false; }
-        o->tables_tr.resize((size_t)o->data_dim * 256);  // src/pq.cpp:158-166
+            if (o->chunk_offsets[i] > o->chunk_offsets[i + 1] || o->chunk_offsets[i + 1] > (uint32_t)o->ndims) { *err = pivots + ": chunk offsets out of range"; return false; }
+        o->tables_tr.resize((size_t)o->ndims * 256);  // src/pq.cpp:158-166
         for (int i = 0; i < 256; i++)
-            for (int j = 0; j < o->data_dim; j++) o->tables_tr[(size_t)j * 256 + i] = tables[(size_t)i * o->data_dim + j];
+            for (int j = 0; j < o->ndims; j++) o->tables_tr[(size_t)j * 256 + i] = tables[(size_t)i * o->ndims + j];
+    }
+    return true;
+}
+
+bool read_diskann_index(const char* index_prefix, const char* partition_prefix, int metric, VamanaHost* o, std::string* err) {
+    const std::string p = index_prefix ? index_prefix : "";
+    const std::string pp = partition_prefix ? partition_prefix : "";
+    if (p.empty()) { *err = "index_prefix is empty"; return false; }
+    if (metric < 0 || metric > 2) { *err = "metric must be 0 (l2), 1 (mips) or 2 (cosine)"; return false; }
+    o->metric = metric;
+    o->partitioned = !pp.empty();
+    const std::string pivots = p + "_pq_pivots.bin", compressed = p + "_pq_compressed.bin", disk = p + "_disk.index";
+    if (exists(pivots + "_rotation_matrix.bin")) { *err = "OPQ rotation matrix is not supported"; return false; }
+    if (!o->partitioned && exists(disk + "_pq_pivots.bin")) { *err = "disk-PQ indexes are not supported"; return false; }
+    if (exists(disk + "_labels.txt")) { *err = "filtered (labelled) indexes are not supported"; return false; }
+    int64_t r = 0, c = 0;
+    {   // ---- PQ codes + pivots
+        PqHost pq;
+        if (!read_pq_files(pivots, compressed, &pq, err)) return false;
+        o->n = pq.n; o->n_chunks = pq.n_chunks; o->data_dim = pq.ndims;
+        o->codes.swap(pq.codes); o->tables_tr.swap(pq.tables_tr); o->centroid.swap(pq.centroid); o->chunk_offsets.swap(pq.chunk_offsets);
     }
     const int D = o->data_dim;
     uint64_t medoid_on_file = 0;

@@ -26,6 +26,17 @@ struct VamanaHost {
     int64_t n_edges = 0;
 };
 
+// product-quantisation tables + codes of a DiskANN-format file pair
+struct PqHost {
+    int64_t n = 0;
+    int ndims = 0, n_chunks = 0;
+    std::vector<uint8_t> codes;          // [n, n_chunks]
+    std::vector<float> tables_tr;        // [ndims, 256]
+    std::vector<float> centroid;         // [ndims]
+    std::vector<uint32_t> chunk_offsets; // [n_chunks + 1]
+};
+bool read_pq_files(const std::string& pivots_path, const std::string& compressed_path, PqHost* out, std::string* err);
+
 bool read_diskann_index(const char* index_prefix, const char* partition_prefix, int metric, VamanaHost* out, std::string* err);
 
 }  // namespace lb2

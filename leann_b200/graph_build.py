@@ -320,7 +320,7 @@ def build_hnsw_graph(emb, M: int = 32, metric: str = "mips", seed: int = 12345, 
 
 @torch.no_grad()
 def _select_rows(xs: torch.Tensor, me: torch.Tensor, cand: torch.Tensor, cd: torch.Tensor, keep: int, metric_ip: bool,
-                 sq: torch.Tensor | None, block: int = 4096):
+                 sq: torch.Tensor | None, block: int = 4096, fill: int = 0):
     """Neighbour-selection heuristic (HNSW::shrink_neighbor_list, faiss/impl/HNSW.cpp:426-468) over candidate rows
     sorted by distance (cand int32 [b, K] -1 padded at the end, cd fp32 [b, K]).  Pairwise candidate distances come from
     one batched GEMM per row block; the sequential keep/drop scan is lb2_build_select (one warp per row).
@@ -344,7 +344,7 @@ def _select_rows(xs: torch.Tensor, me: torch.Tensor, cand: torch.Tensor, cd: tor
         ci = cand[b0:b1].contiguous()
         di = cd[b0:b1].contiguous()
         capi.build_select(pd.data_ptr(), False, di.data_ptr(), ci.data_ptr(), b1 - b0, K, keep,
-                          out_i[b0:b1].data_ptr(), out_d[b0:b1].data_ptr())
+                          out_i[b0:b1].data_ptr(), out_d[b0:b1].data_ptr(), fill=fill)
         del cv, pd
     return out_i, out_d
 
@@ -402,14 +402,15 @@ def upper_level_arrays(levels: np.ndarray, upper: dict, M: int, dev):
 @torch.no_grad()
 def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
                                  ef_construction: int = 200, growth: float = 0.25, min_seed: int = 20000,
-                                 max_batch: int = 1 << 20, sweeps: int = 0, verbose: bool = False) -> CSRGraph:
+                                 max_batch: int = 1 << 20, sweeps: int = 0, fill: int = 0, verbose: bool = False) -> CSRGraph:
     """HNSW construction the way the reference does it — every point is inserted by searching the graph built so far
     (hnsw_add_vertices, faiss/IndexHNSW.cpp:59-280: upper levels first, level-0-only points last) — run batch-parallel
     on the GPU: the points of a batch search concurrently (lb2_build_insert_search, one warp per point), select their
     links with the heuristic (lb2_build_select) and their reverse links are merged per target.  A batch never exceeds
     `growth` x the points already inserted, so a new point misses at most that share of its potential neighbours at
     insertion time; later insertions link back to it, and `sweeps` optional passes re-search every point on the finished
-    graph to repair what the batches missed.  The upper levels (3 % of the points) and the level-0 seed among them are
+    graph to repair what the batches missed.  `fill` > 0 tops forward lists up to that many links with the nearest
+    rejected candidates (the reference's keep_max_size_level0 idea with a settable floor).  The upper levels (3 % of the points) and the level-0 seed among them are
     built exactly (brute-force lists) by the batch builder above.  CUDA only."""
     from . import capi
 
@@ -471,7 +472,7 @@ def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: i
         b = int(min(max(1024, growth * n_in), max_batch, len(rest) - pos))
         pts = rest_t[pos:pos + b].contiguous()
         ci, cd = search(pts)
-        fi, fd = _select_rows(xs, pts, ci, cd, cap0, metric_ip, sq)
+        fi, fd = _select_rows(xs, pts, ci, cd, cap0, metric_ip, sq, fill=fill)
         p64 = pts.long()
         adj[p64] = fi
         adjd[p64] = fd
@@ -498,7 +499,7 @@ def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: i
             o = torch.argsort(md, dim=1, stable=True)
             mi, md = torch.gather(mi, 1, o), torch.gather(md, 1, o)
             old = adj[p64].clone()
-            fi, fd = _select_rows(xs, pts, mi.contiguous(), md.contiguous(), cap0, metric_ip, sq)
+            fi, fd = _select_rows(xs, pts, mi.contiguous(), md.contiguous(), cap0, metric_ip, sq, fill=fill)
             adj[p64] = fi
             adjd[p64] = fd
             # reverse links for edges that are new

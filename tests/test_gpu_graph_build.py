@@ -47,12 +47,21 @@ def test_select_kernel_is_the_reference_heuristic():
         pref = p.float().cpu().numpy()
         oi = torch.empty((b, keep), dtype=torch.int32, device="cuda")
         od = torch.empty((b, keep), dtype=torch.float32, device="cuda")
-        capi.build_select(p.data_ptr(), as_f32, torch.from_numpy(dn).cuda().data_ptr(), torch.from_numpy(cand).cuda().data_ptr(),
-                          b, K, keep, oi.data_ptr(), od.data_ptr())
+        d_dn, d_cand = torch.from_numpy(dn).cuda(), torch.from_numpy(cand).cuda()  # keep the device copies alive across the call
+        capi.build_select(p.data_ptr(), as_f32, d_dn.data_ptr(), d_cand.data_ptr(), b, K, keep, oi.data_ptr(), od.data_ptr())
         torch.cuda.synchronize()
         got = oi.cpu().numpy()
         for r in range(b):
             want = shrink_reference(pref[r], dn[r], cand[r], keep)
+            assert got[r, :len(want)].tolist() == want and (got[r, len(want):] == -1).all()
+        # fill: rejected candidates, nearest first, top the list up to the floor
+        capi.build_select(p.data_ptr(), as_f32, d_dn.data_ptr(), d_cand.data_ptr(), b, K, keep, oi.data_ptr(), od.data_ptr(), fill=8)
+        torch.cuda.synchronize()
+        got = oi.cpu().numpy()
+        for r in range(b):
+            want = shrink_reference(pref[r], dn[r], cand[r], keep)
+            rest = [int(c) for c in cand[r] if c >= 0 and int(c) not in want]
+            want = want + rest[: max(0, 8 - len(want))]
             assert got[r, :len(want)].tolist() == want and (got[r, len(want):] == -1).all()
 
 
