@@ -15,8 +15,9 @@
 //                   row maximum, pass 2 p = 2^((s - m) * scale * log2 e), row sum, fp16 P written back to TMEM
 //                   IN PLACE over the columns of S already consumed (tcgen05.st), zeros for keys >= L.  After the
 //                   P.V MMAs: O from TMEM -> * 1/sum -> fp16 -> ctx[token][h * 32 ..] (64 B per row).
-// TMEM columns of a CTA: S = [0, Lp) fp32, P = [0, Lp / 2) packed fp16 (aliases S), O = [128, 160) (aliases dead S
-// columns; the first P.V MMA overwrites).  Barriers: full/empty (smem ring), s_ready, p_ready, o_ready, t_free.
+// TMEM columns of a CTA: S = [0, Lp) fp32, P = [0, Lp / 2) packed fp16 (aliases S), two O accumulators [192, 224) and
+// [224, 256) (alias the top S columns of passages longer than 192 keys only).  Barriers: full/empty (smem ring), s_ready,
+// p_ready, o_ready[2], o_free[2].
 // Bound: the softmax (MUFU ex2 + issue slots), not the tensor pipe — 4.L.h flops per token are 5 % of the layer.
 #include <cuda_fp16.h>
 
@@ -39,7 +40,8 @@ constexpr int ATC_STAGES = 2;
 constexpr int ATC_BAR_OFFSET = ATC_STAGES * ATC_STAGE_BYTES;
 constexpr int ATC_SMEM = ATC_BAR_OFFSET + 16 * 8 + 16 + 1024;
 constexpr int ATC_TMEM_COLS = 256;
-constexpr int ATC_O_COL = 128;
+constexpr int ATC_O_COL0 = 192;  // two O accumulators of 32 columns at the top of the allocation
+constexpr int ATC_LONG = 192;    // an item whose S needs more columns than this overlaps them ("long" item)
 
 __device__ __forceinline__ float ex2f(float x) {
     float y;
@@ -61,6 +63,12 @@ __global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_len, i
     for (int i = 0; i < nb; i++) items[base + i] = s * 8 + i;
 }
 
+// Pipeline of one CTA over its items i = 0, 1, ... (two CTAs per SM interleave):
+//   MMA warp     : S(0) | for i: wait P(i) -> P.V(i) into O[i & 1] -> S(i + 1) right behind it (the tensor pipe runs the
+//                  MMAs in issue order, so S(i + 1) may overwrite the columns of P(i) without a barrier)
+//   softmax warps: for i: wait S(i) -> softmax -> P(i) | read O(i - 1) out while P.V(i) and S(i + 1) execute
+// so the chain per item is softmax -> P.V + S, and the O read-out, the TMA loads and the other CTA's softmax fill the gaps.
+// A long item (S wider than 192 columns) would overwrite the O accumulators: both sides drain the pending read-outs first.
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
                     const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
@@ -72,12 +80,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     uint64_t* empty_bar = full_bar + ATC_STAGES;
     uint64_t* s_ready = empty_bar + ATC_STAGES;
     uint64_t* p_ready = s_ready + 1;
-    uint64_t* o_ready = p_ready + 1;
-    uint64_t* t_free = o_ready + 1;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_free + 1);
+    uint64_t* o_ready = p_ready + 1;  // [2]
+    uint64_t* o_free = o_ready + 2;   // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = *n_items * heads;
+    const int n_it = total > static_cast<int>(blockIdx.x) ? (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tmap(&tmap_qk);
@@ -88,8 +97,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
         }
         ptx::mbar_init(s_ready, 1);
         ptx::mbar_init(p_ready, 4);
-        ptx::mbar_init(o_ready, 1);
-        ptx::mbar_init(t_free, 4);
+        for (int i = 0; i < 2; i++) {
+            ptx::mbar_init(&o_ready[i], 1);
+            ptx::mbar_init(&o_free[i], 4);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 5) {
@@ -104,8 +115,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     if (warp == 4) {
         if (lane == 0) {
             // ===== TMA producer
-            int it = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
+            for (int it = 0; it < n_it; it++) {
+                const int w = blockIdx.x + it * gridDim.x;
                 const int stage = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 const int item = items[w / heads], h = w % heads;
@@ -124,56 +135,97 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        if (lane == 0 && n_it > 0) {
             // ===== MMA issuer
-            int it = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
-                const int stage = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                const int item = items[w / heads];
-                const int s = item >> 3, qb = item & 7;
-                const int L = seq_len[s];
-                const int Lp = (L + 15) & ~15;
-                ptx::mbar_wait(&full_bar[stage], ph);
-                ptx::mbar_wait(t_free, (it & 1) ^ 1);  // the previous item's O has been read out of TMEM
-                ptx::tc_fence_after();
-                const uint32_t qk = ptx::smem_u32(smem + stage * ATC_STAGE_BYTES);
+            auto issue_s = [&](int it) {
+                const int item = items[(blockIdx.x + it * gridDim.x) / heads];
+                const int qb = item & 7;
+                const int Lp = (seq_len[item >> 3] + 15) & ~15;
+                const uint32_t qk = ptx::smem_u32(smem + (it & 1) * ATC_STAGE_BYTES);
                 const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + qb * ATC_TM * 128);
                 const uint64_t b_desc = ptx::make_sw128_kmajor_desc(qk) + 4;  // the k half of the (q | k) rows: +64 B
                 const uint32_t idesc_s = ptx::make_idesc_f16(ATC_TM, Lp);
 #pragma unroll
                 for (int k = 0; k < ATC_HD / 16; k++) ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0);
                 ptx::umma_commit(s_ready);
+            };
+            ptx::mbar_wait(&full_bar[0], 0);
+            ptx::tc_fence_after();
+            issue_s(0);
+            for (int it = 0; it < n_it; it++) {
+                const int stage = it & 1, b = it & 1;
+                const int Lp = (seq_len[items[(blockIdx.x + it * gridDim.x) / heads] >> 3] + 15) & ~15;
                 ptx::mbar_wait(p_ready, it & 1);
+                ptx::mbar_wait(&o_free[b], ((it >> 1) & 1) ^ 1);  // the previous user of this O accumulator has been read out
                 ptx::tc_fence_after();
-                const uint32_t vb = qk + ATC_QK_BYTES;
+                const uint32_t vb = ptx::smem_u32(smem + stage * ATC_STAGE_BYTES) + ATC_QK_BYTES;
                 const uint32_t idesc_o = ptx::make_idesc_f16(ATC_TM, ATC_HD) | ptx::IDESC_B_MN_MAJOR;
+                const uint32_t o_tmem = tmem_base + ATC_O_COL0 + 32 * b;
                 for (int j = 0; j < Lp / 16; j++)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (1 KB) of V
-                    ptx::umma_f16_ts(tmem_base + ATC_O_COL, tmem_base + 8 * j, ptx::make_mn_major_desc(vb + j * 1024, 64), idesc_o,
-                                     j != 0);
-                ptx::umma_commit(o_ready);
+                    ptx::umma_f16_ts(o_tmem, tmem_base + 8 * j, ptx::make_mn_major_desc(vb + j * 1024, 64), idesc_o, j != 0);
+                ptx::umma_commit(&o_ready[b]);
                 ptx::umma_commit(&empty_bar[stage]);
+                if (it + 1 < n_it) {
+                    const int Ln = seq_len[items[(blockIdx.x + (it + 1) * gridDim.x) / heads] >> 3];
+                    ptx::mbar_wait(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                    if (((Ln + 15) & ~15) > ATC_LONG) {  // S(it + 1) covers the O accumulators: O(it) and O(it - 1) must be out
+                        ptx::mbar_wait(&o_free[b], (it >> 1) & 1);
+                        if (it >= 1) ptx::mbar_wait(&o_free[b ^ 1], ((it - 1) >> 1) & 1);
+                    }
+                    ptx::tc_fence_after();
+                    issue_s(it + 1);
+                }
             }
         }
     } else {
         // ===== softmax + output: thread = query row
         const float scale_log2 = rsqrtf(static_cast<float>(ATC_HD)) * 1.4426950408889634f;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-        int it = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
+        float inv_sum[2] = {0.f, 0.f};
+        long long out_off[2] = {-1, -1};  // element offset of this thread's output row, -1 = row beyond the passage
+        int pend = 0;                     // first item whose O has not been read out yet
+
+        auto readout = [&](int j) {
+            const int b = j & 1;
+            uint32_t o[32];
+            ptx::mbar_wait(&o_ready[b], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32(taddr + ATC_O_COL0 + 32 * b, o);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&o_free[b]);
+            const long long off = b ? out_off[1] : out_off[0];
+            if (off >= 0) {
+                const float inv = b ? inv_sum[1] : inv_sum[0];
+                uint4* dst = reinterpret_cast<uint4*>(ctx + off);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; v4++) {
+                    uint4 ov;
+                    ov.x = pack2(__uint_as_float(o[8 * v4 + 0]) * inv, __uint_as_float(o[8 * v4 + 1]) * inv);
+                    ov.y = pack2(__uint_as_float(o[8 * v4 + 2]) * inv, __uint_as_float(o[8 * v4 + 3]) * inv);
+                    ov.z = pack2(__uint_as_float(o[8 * v4 + 4]) * inv, __uint_as_float(o[8 * v4 + 5]) * inv);
+                    ov.w = pack2(__uint_as_float(o[8 * v4 + 6]) * inv, __uint_as_float(o[8 * v4 + 7]) * inv);
+                    dst[v4] = ov;
+                }
+            }
+        };
+
+        for (int it = 0; it < n_it; it++) {
+            const int w = blockIdx.x + it * gridDim.x;
             const int item = items[w / heads], h = w % heads;
             const int s = item >> 3, qb = item & 7;
             const int L = seq_len[s];
             const int q = qb * ATC_TM + threadIdx.x;
             const int nch = (L + 31) >> 5;
+            if (((L + 15) & ~15) > ATC_LONG)  // the MMA warp waits for these before it may issue S(it)
+                while (pend < it) readout(pend++);
             ptx::mbar_wait(s_ready, it & 1);
             ptx::tc_fence_after();
-            uint32_t r[32];
-            // pass 1: row maximum over the L valid keys
+            uint32_t ra[32], rb[32];
+            // pass 1: row maximum over the L valid keys (TMEM loads one chunk ahead of the arithmetic)
             float m = -INFINITY;
-            for (int c = 0; c < nch; c++) {
-                ptx::tmem_ld_32x32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
+            auto max_chunk = [&](int c, const uint32_t (&r)[32]) {
                 if (c * 32 + 32 <= L) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
@@ -181,13 +233,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; j++) m = (c * 32 + j < L) ? fmaxf(m, __uint_as_float(r[j])) : m;
                 }
+            };
+            ptx::tmem_ld_32x32(taddr, ra);
+            for (int c = 0; c < nch; c += 2) {
+                ptx::tmem_ld_wait();
+                if (c + 1 < nch) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+                max_chunk(c, ra);
+                if (c + 1 < nch) {
+                    ptx::tmem_ld_wait();
+                    if (c + 2 < nch) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                    max_chunk(c + 1, rb);
+                }
             }
             // pass 2: probabilities (fp16, back into TMEM over the consumed S columns), row sum
             const float ms = m * scale_log2;
             float sum = 0.f;
-            for (int c = 0; c < nch; c++) {
-                ptx::tmem_ld_32x32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
+            auto exp_chunk = [&](int c, const uint32_t (&r)[32]) {
                 uint32_t pk[16];
                 if (c * 32 + 32 <= L) {
 #pragma unroll
@@ -209,33 +270,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                     }
                 }
                 ptx::tmem_st_32x16(taddr + c * 16, pk);
+            };
+            ptx::tmem_ld_32x32(taddr, ra);
+            for (int c = 0; c < nch; c += 2) {
+                ptx::tmem_ld_wait();
+                if (c + 1 < nch) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+                exp_chunk(c, ra);
+                if (c + 1 < nch) {
+                    ptx::tmem_ld_wait();
+                    if (c + 2 < nch) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                    exp_chunk(c + 1, rb);
+                }
             }
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
-            // O = P . V
-            ptx::mbar_wait(o_ready, it & 1);
-            ptx::tc_fence_after();
-            ptx::tmem_ld_32x32(taddr + ATC_O_COL, r);
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(t_free);
-            if (q < L) {
-                const float inv = 1.0f / sum;
-                uint4* dst = reinterpret_cast<uint4*>(ctx + static_cast<size_t>(seq_start[s] - row_base + q) * hidden + h * ATC_HD);
-#pragma unroll
-                for (int v4 = 0; v4 < 4; v4++) {
-                    uint4 o;
-                    o.x = pack2(__uint_as_float(r[8 * v4 + 0]) * inv, __uint_as_float(r[8 * v4 + 1]) * inv);
-                    o.y = pack2(__uint_as_float(r[8 * v4 + 2]) * inv, __uint_as_float(r[8 * v4 + 3]) * inv);
-                    o.z = pack2(__uint_as_float(r[8 * v4 + 4]) * inv, __uint_as_float(r[8 * v4 + 5]) * inv);
-                    o.w = pack2(__uint_as_float(r[8 * v4 + 6]) * inv, __uint_as_float(r[8 * v4 + 7]) * inv);
-                    dst[v4] = o;
-                }
-            }
+            const float inv = 1.0f / sum;
+            const long long off = q < L ? static_cast<long long>(seq_start[s] - row_base + q) * hidden + h * ATC_HD : -1;
+            if (it & 1) { inv_sum[1] = inv; out_off[1] = off; } else { inv_sum[0] = inv; out_off[0] = off; }
+            while (pend < it) readout(pend++);  // O(it - 1): its P.V was issued long ago; runs while P.V(it) and S(it + 1) execute
         }
+        while (pend < n_it) readout(pend++);
     }
 
     ptx::tc_fence_before();

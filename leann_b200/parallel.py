@@ -33,18 +33,20 @@ def sharded_search(local_search: Callable[[np.ndarray], tuple[np.ndarray, np.nda
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
     cap = (nq + world - 1) // world  # equal-sized buffers for all_gather
-    bufD = torch.zeros((cap, k), dtype=torch.float32, device=device)
-    bufI = torch.full((cap, k), -1, dtype=torch.int64, device=device)
-    bufD[: hi - lo] = torch.from_numpy(np.ascontiguousarray(D_loc)).to(device)
-    bufI[: hi - lo] = torch.from_numpy(np.ascontiguousarray(I_loc)).to(device)
-    outD = [torch.empty_like(bufD) for _ in range(world)]
-    outI = [torch.empty_like(bufI) for _ in range(world)]
-    dist.all_gather(outD, bufD, group=group)
-    dist.all_gather(outI, bufI, group=group)
+    # ONE collective per call: labels and distances travel together as 12-byte (int64, float32) records
+    rec = np.dtype([("i", "<i8"), ("d", "<f4")])
+    mine = np.zeros((cap, k), rec)
+    mine["i"] = -1
+    mine["i"][: hi - lo] = I_loc
+    mine["d"][: hi - lo] = D_loc
+    buf = torch.from_numpy(mine.view(np.uint8).reshape(cap, k * rec.itemsize)).to(device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
     D = np.empty((nq, k), np.float32)
     I = np.empty((nq, k), np.int64)
     for r in range(world):
         a, b = shard_bounds(nq, world, r)
-        D[a:b] = outD[r][: b - a].cpu().numpy()
-        I[a:b] = outI[r][: b - a].cpu().numpy()
+        got = out[r].cpu().numpy().reshape(-1).view(rec).reshape(cap, k)
+        D[a:b] = got["d"][: b - a]
+        I[a:b] = got["i"][: b - a]
     return D, I

@@ -15,8 +15,11 @@ variants = sys.argv[2:] or ["base:", "sweep1:sweeps=1", "fill16:fill=16", "fill2
 preset = synth.MINILM_L6
 blob = synth.pack_weights(preset, synth.synthetic_weights(preset, 0))
 t0 = time.time()
-tm, corpus = synth.make_corpus(N, preset.vocab_size, seed=1234, max_len=preset.max_pos, device="cuda:0")
-queries = synth.make_queries(tm, 4096, seed=4321)
+import os
+TS = int(os.environ.get("LB2_TOPIC_SIZE", 32)); PT = float(os.environ.get("LB2_P_TOPIC", 0.80)); PS = float(os.environ.get("LB2_P_SUPER", 0.10))
+print(f"corpus: {N} passages, topic size {TS}, mix topic/super/background = {PT}/{PS}/{1-PT-PS:.2f}", flush=True)
+tm, corpus = synth.make_corpus(N, preset.vocab_size, seed=1234, max_len=preset.max_pos, device="cuda:0", n_topics=max(4, N // TS), p_topic=PT, p_super=PS)
+queries = synth.make_queries(tm, 4096, seed=4321, p_topic=PT, p_super=PS)
 work = Path(tempfile.mkdtemp())
 csr.write_compact_index(str(work / "stub.index"), stub_graph(N, 384))
 enc = capi.Index(str(work / "stub.index"), 0)
