@@ -337,7 +337,7 @@ def run_b200(args):
             agg[key] += st[key]
         agg["launches"] += st["n_kernel_launches"]
         agg["steps"] += st["n_steps"]
-        agg["passes"] += (st["n_kernel_launches"] - 1 - 2 * st["n_steps"]) // (3 + 7 * W["preset"].layers)
+        agg["passes"] += st["n_encoder_passes"]
         I = np.array([[int(x) for x in row] for row in out["labels"]], np.int64)
         recalls.append(recall_at_k(I, W["gt"][ids]))
     barrier()

@@ -74,6 +74,7 @@ typedef struct {
     double gemm_flops;       /* algorithmic flops of those GEMMs                                    */
     double attention_ms;     /* attention kernels (profiling on)                                    */
     double norm_ms;          /* LayerNorm kernels (profiling on)                                    */
+    int64_t n_encoder_passes;/* encoder passes (each <= passages_per_pass passages) of the call           */
 } lb2_search_stats;
 
 typedef struct {
@@ -254,6 +255,9 @@ int lb2_build_select(const void* d_pd, int32_t pd_is_f32, const float* d_dn, con
 /* ---- kernel-level hooks for the unit tests (device pointers, default stream, synchronous) ---- */
 int lb2_test_gemm_f16(const void* dA, const void* dW, const float* dbias, const void* dres, void* dC, int M, int N,
                       int K, int epilogue /* 0 bias, 1 bias+gelu, 2 bias+residual */);
+/* C = LayerNorm(A . W^T + bias + residual) * gamma + beta, N = 384 (the fused residual projections of a BERT block) */
+int lb2_test_gemm_res_ln_f16(const void* dA, const void* dW, const float* dbias, const void* dres, const float* dgamma,
+                             const float* dbeta, float eps, void* dC, int M, int N, int K);
 int lb2_test_layernorm_f16(const void* din, const float* dg, const float* db, void* dout, int rows, int hidden,
                            float eps);
 /* qkv: HEAD-MAJOR packed [heads][n_tokens][3*head_dim] fp16 (q|k|v per token), n_tokens = sum(len);

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "lb2_diskann_open", "lb2_diskann_info", "lb2_diskann_default_params", "lb2_diskann_search",
     "lb2_diskann_search_device", "lb2_diskann_last_expansions",
     "lb2_build_insert_search", "lb2_build_workspace_bytes", "lb2_build_select",
-    "lb2_test_gemm_f16", "lb2_test_gemm_grouped_f16", "lb2_test_layernorm_f16", "lb2_test_attention_f16",
+    "lb2_test_gemm_f16", "lb2_test_gemm_grouped_f16", "lb2_test_layernorm_f16", "lb2_test_gemm_res_ln_f16", "lb2_test_attention_f16",
 ]
 
 
@@ -37,7 +37,7 @@ class SearchStats(C.Structure):
     _fields_ = [("ndis", C.c_int64), ("nhops", C.c_int64), ("n_recomputed", C.c_int64), ("n_requested", C.c_int64),
                 ("n_tokens", C.c_int64), ("n_steps", C.c_int64), ("n_kernel_launches", C.c_int64),
                 ("gpu_ms", C.c_double), ("encoder_ms", C.c_double), ("gemm_ms", C.c_double),
-                ("gemm_flops", C.c_double), ("attention_ms", C.c_double), ("norm_ms", C.c_double)]
+                ("gemm_flops", C.c_double), ("attention_ms", C.c_double), ("norm_ms", C.c_double), ("n_encoder_passes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -121,6 +121,8 @@ def load():
     lib.lb2_diskann_last_expansions.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.lb2_test_gemm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int]
+    lib.lb2_test_gemm_res_ln_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                             C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.lb2_test_layernorm_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
     lib.lb2_test_attention_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lb2_test_gemm_grouped_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]

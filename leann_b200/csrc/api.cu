@@ -295,7 +295,11 @@ int next_pow2(int v) {
     return p;
 }
 
-int encoder_kernels_per_pass(const Encoder& e) { return 3 + e.cfg.layers * 7; }  // embed, work list, pool + 7 per layer
+// embed, work list, pool + per layer: 4 GEMMs, attention, and 2 LayerNorm kernels unless they ride in the GEMM epilogues
+int encoder_kernels_per_pass(const Encoder& e) {
+    const bool fused_ln = e.cfg.hidden == 2 * gemm_block_n() && !(getenv("LB2_FUSED_LN") && atoi(getenv("LB2_FUSED_LN")) == 0);
+    return 3 + e.cfg.layers * (fused_ln ? 5 : 7);
+}
 
 int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_D, int64_t* d_I,
                 const lb2_search_params* prm, lb2_search_stats* stats) {
@@ -378,7 +382,7 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     g_prof_on = x->profile_gemm;
     cudaEventRecord(x->ev_total.get(), st);
     if (!launch_init_slots(st, s)) return LB2_ERR_CUDA;
-    long long launches = 1, steps = 0, n_recomputed = 0, n_tokens = 0;
+    long long launches = 1, steps = 0, n_recomputed = 0, n_tokens = 0, n_passes = 0;
 
     if (!recompute) {
         s.epoch = 1;
@@ -422,6 +426,7 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
                                      row_base, n_seq, n_tok, x->d_E + ((size_t)s.row_base_hop + first) * x->g.d))
                     return LB2_ERR_CUDA;
                 launches += encoder_kernels_per_pass(x->enc);
+                n_passes++;
             }
             cudaEventRecord(x->ev_enc.get(), st);
             rows_this_call += c.n_unique;
@@ -463,6 +468,7 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
         stats->gemm_flops = g_gemm_flops;
         stats->attention_ms = g_prof_pool[PROF_ATTN].total_ms;
         stats->norm_ms = g_prof_pool[PROF_NORM].total_ms;
+        stats->n_encoder_passes = n_passes;
     }
     return LB2_OK;
 }
@@ -1159,6 +1165,19 @@ int lb2_test_gemm_grouped_f16(const void* dA, const void* dW, const float* dbias
         return LB2_ERR_CUDA;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
+    return LB2_OK;
+}
+
+int lb2_test_gemm_res_ln_f16(const void* dA, const void* dW, const float* dbias, const void* dres, const float* dgamma,
+                             const float* dbeta, float eps, void* dC, int M, int N, int K) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool ok = gemm_f16_res_ln(0, (const __half*)dA, nullptr, (const __half*)dW, dbias, (const __half*)dres, dgamma, dbeta, eps,
+                                    (__half*)dC, M, N, K, sms);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (!ok) return LB2_ERR_ARG;
+    if (e != cudaSuccess) { set_error("gemm_res_ln: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     return LB2_OK;
 }
 

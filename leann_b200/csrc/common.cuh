@@ -28,6 +28,9 @@ bool make_tmap_f16_3d(CUtensorMap* map, const void* ptr, uint64_t row_elems, uin
                       uint32_t box_rows);
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
               const __half* residual, __half* C, int M, int N, int K, int epi, int num_sms, int c_group = 0);
+bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
+                     const __half* residual, const float* gamma, const float* beta, float eps, __half* C, int M, int N, int K,
+                     int num_sms);
 int gemm_block_n();
 // optional per-kernel-class timing with CUDA events (api.cu owns the pools; no-ops unless
 // LB2_PROFILE_GEMM=1): category 0 = tcgen05 GEMMs, 1 = attention, 2 = LayerNorm / embed / pool

@@ -631,6 +631,10 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
         prof_end(st, PROF_GEMM, 2.0 * T * (double)N * K);
         return ok;
     };
+    // hidden = 2 GEMM n-tiles: the residual projections carry their LayerNorm (gemm_f16_res_ln); LB2_FUSED_LN=0 keeps the
+    // separate bandwidth-bound LayerNorm kernel (A/B profiling).  hidden 768 (bge-base) always takes the unfused path.
+    static const bool fused_ln_env = !(getenv("LB2_FUSED_LN") && atoi(getenv("LB2_FUSED_LN")) == 0);
+    const bool fused_ln = fused_ln_env && H == 2 * gemm_block_n();
     for (int l = 0; l < c.layers; l++) {
         const LayerWeights& w = enc->layers[l];
         if (!gemm(enc->x, &w.tm_qkv, w.w_qkv, w.b_qkv, nullptr, enc->qkv, 3 * H, H, EPI_BIAS, 3 * (H / c.heads))) return false;
@@ -639,6 +643,20 @@ bool encoder_forward(Encoder* enc, cudaStream_t st, const uint16_t* tok_store, c
                               row_base, c.max_pos, n_seq, T, H, c.heads, enc->ctx, l == 0))
             return false;
         prof_end(st, PROF_ATTN, 0);
+        if (fused_ln) {
+            // hidden 384: Linear + residual + LayerNorm in ONE kernel (gemm_f16_ln_kernel): x -> y -> x ping-pong, the
+            // pre-norm activation never touches HBM
+            prof_begin(st, PROF_GEMM);
+            bool ok = gemm_f16_res_ln(st, enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, w.ln1_g, w.ln1_b, c.ln_eps, enc->y, T, H, H, sms);
+            prof_end(st, PROF_GEMM, 2.0 * T * (double)H * H);
+            if (!ok) return false;
+            if (!gemm(enc->y, &w.tm_1, w.w_1, w.b_1, nullptr, enc->ffn, F, H, EPI_BIAS_GELU)) return false;
+            prof_begin(st, PROF_GEMM);
+            ok = gemm_f16_res_ln(st, enc->ffn, &w.tm_2, w.w_2, w.b_2, enc->y, w.ln2_g, w.ln2_b, c.ln_eps, enc->x, T, H, F, sms);
+            prof_end(st, PROF_GEMM, 2.0 * T * (double)H * F);
+            if (!ok) return false;
+            continue;
+        }
         if (!gemm(enc->ctx, &w.tm_o, w.w_o, w.b_o, enc->x, enc->y, H, H, EPI_BIAS_RES)) return false;
         prof_begin(st, PROF_NORM);
         if (!launch_layernorm(st, enc->y, w.ln1_g, w.ln1_b, enc->x, T, H, c.ln_eps)) return false;

@@ -270,6 +270,252 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Residual projection with LayerNorm fused into the epilogue (hidden = 2 * BLOCK_N = 384 only):
+//     x_out = LayerNorm(A . W^T + bias + residual) * gamma + beta
+// i.e. the attention-output / FFN-down Linear, the residual add and BertSelfOutput / BertOutput's LayerNorm of one BERT
+// block in one kernel: the pre-norm activation never goes to HBM (the separate LayerNorm kernel read and wrote 1.5 KB per
+// token twice per layer).  A CTA owns WHOLE rows: it computes the two 192-column halves of a 128-row block back to back
+// (two TMEM accumulator stages), the epilogue keeps both halves as fp16 in shared memory (the TMA-store staging boxes,
+// 96 KB), accumulates per-row sum / sum of squares on the fp16-rounded values (the numerics of the unfused pipeline, which
+// normalised the fp16 tensor), exchanges them between the two warps that share a row, normalises in place and stores.
+// Same producer / MMA warps and mbarrier pipelines as gemm_f16_tn_kernel; 3 smem stages instead of 4 to make room.
+template <int BLOCK_N, int STAGES>
+struct GemmLnSmem {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_CHUNKS = BLOCK_N / 32 / 2;            // 32-column chunks per warp and half
+    static constexpr int TILE_BOX_BYTES = EPI_WARPS * EPI_CHUNKS * 2048;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = 2 * TILE_BOX_BYTES;           // both column halves of the row block
+    static constexpr int STAT_OFFSET = EPI_OFFSET + EPI_BYTES;
+    static constexpr int STAT_BYTES = EPI_WARPS * 32 * 8;
+    static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+                   const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   int M, int K) {
+    using L = GemmLnSmem<BLOCK_N, STAGES>;
+    constexpr int N = 2 * BLOCK_N;
+    constexpr int TMEM_COLS = 512;
+    static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* res_bar = tmem_empty + 2;  // [2][EPI_WARPS] residual boxes of a half landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    const int num_k = K / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_c);
+        ptx::prefetch_tmap(&tmap_r);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            ptx::mbar_init(&tmem_full[i], 1);
+            ptx::mbar_init(&tmem_empty[i], EPI_WARPS);
+        }
+        for (int i = 0; i < 2 * EPI_WARPS; i++) ptx::mbar_init(&res_bar[i], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer: row block m, column halves 0 and 1 back to back
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x) {
+                for (int n_blk = 0; n_blk < 2; n_blk++) {
+                    for (int kb = 0; kb < num_k; kb++) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                        uint8_t* sb = sa + L::A_BYTES;
+                        ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer: half n accumulates in TMEM stage n
+            constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, it++) {
+                for (int as = 0; as < 2; as++) {
+                    ptx::mbar_wait(&tmem_empty[as], (it & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                    for (int kb = 0; kb < num_k; kb++) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+                        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(sa);
+                        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(sa + L::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+                            ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::umma_commit(&tmem_full[as]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps; warp (quarter, half) owns rows [32 quarter, +32) and, in each column half of the row block,
+        // the 96 columns [96 half, +96) as three 32-column chunks.  Thread = row.
+        const int quarter = warp & 3;
+        const int ew = warp - 4;
+        const int half = ew >> 2;
+        constexpr int NCH = L::EPI_CHUNKS;
+        const int swz = (lane >> 1) & 3;
+        float2* stat = reinterpret_cast<float2*>(smem + L::STAT_OFFSET);
+        uint32_t res_phase = 0;
+        int it = 0;
+        for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, it++) {
+            const int row0 = m_blk * BLOCK_M + quarter * 32;
+            if (lane == 0) {
+                ptx::bulk_wait_read<0>();  // the previous row block's stores no longer read the boxes
+                for (int n_blk = 0; n_blk < 2; n_blk++) {
+                    uint8_t* boxes = smem + L::EPI_OFFSET + n_blk * L::TILE_BOX_BYTES + ew * NCH * 2048;
+                    ptx::mbar_expect_tx(&res_bar[n_blk * EPI_WARPS + ew], NCH * 2048);
+#pragma unroll
+                    for (int c = 0; c < NCH; c++)
+                        ptx::tma_load_2d(boxes + c * 2048, &tmap_r, &res_bar[n_blk * EPI_WARPS + ew],
+                                         n_blk * BLOCK_N + half * NCH * 32 + c * 32, row0);
+                }
+            }
+            float sum = 0.f, sumsq = 0.f;
+            // ---- pass 1: accumulator + bias + residual -> fp16 (kept in the boxes), row statistics
+            for (int n_blk = 0; n_blk < 2; n_blk++) {
+                uint8_t* boxes = smem + L::EPI_OFFSET + n_blk * L::TILE_BOX_BYTES + ew * NCH * 2048;
+                const int colbase = n_blk * BLOCK_N + half * NCH * 32;
+                ptx::mbar_wait(&tmem_full[n_blk], it & 1);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + n_blk * BLOCK_N + half * NCH * 32;
+                uint32_t r[2][32];
+                ptx::tmem_ld_32x32(taddr, r[0]);
+                ptx::mbar_wait(&res_bar[n_blk * EPI_WARPS + ew], res_phase);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    ptx::tmem_ld_wait();
+                    if (c + 1 < NCH) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    const uint32_t(&acc)[32] = r[c & 1];
+                    uint8_t* box = boxes + c * 2048 + lane * 64;
+                    const float4* bp = reinterpret_cast<const float4*>(bias + colbase + c * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        uint4* slot = reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4));
+                        const uint4 rv = *slot;
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                        uint4 ov;
+                        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const float4 b4 = __ldg(bp + 2 * j4 + u);
+                            const float2 r0 = __half22float2(rh[2 * u]), r1 = __half22float2(rh[2 * u + 1]);
+                            const __half2 h0 = __floats2half2_rn(__uint_as_float(acc[8 * j4 + 4 * u + 0]) + b4.x + r0.x,
+                                                                 __uint_as_float(acc[8 * j4 + 4 * u + 1]) + b4.y + r0.y);
+                            const __half2 h1 = __floats2half2_rn(__uint_as_float(acc[8 * j4 + 4 * u + 2]) + b4.z + r1.x,
+                                                                 __uint_as_float(acc[8 * j4 + 4 * u + 3]) + b4.w + r1.y);
+                            oh[2 * u] = h0; oh[2 * u + 1] = h1;
+                            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                            sum += (f0.x + f0.y) + (f1.x + f1.y);
+                            sumsq = fmaf(f0.x, f0.x, sumsq); sumsq = fmaf(f0.y, f0.y, sumsq);
+                            sumsq = fmaf(f1.x, f1.x, sumsq); sumsq = fmaf(f1.y, f1.y, sumsq);
+                        }
+                        *slot = ov;
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty[n_blk]);  // accumulator stage free for the next row block
+            }
+            res_phase ^= 1;
+            // ---- the two warps of a row quarter hold the two halves of each row's statistics
+            stat[ew * 32 + lane] = make_float2(sum, sumsq);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            const float2 other = stat[(ew ^ 4) * 32 + lane];
+            const float mean = (sum + other.x) * (1.0f / N);
+            const float var = fmaxf((sumsq + other.y) * (1.0f / N) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // stat[] may be overwritten by the next row block
+            // ---- pass 2: normalise in place, store
+            for (int n_blk = 0; n_blk < 2; n_blk++) {
+                uint8_t* boxes = smem + L::EPI_OFFSET + n_blk * L::TILE_BOX_BYTES + ew * NCH * 2048;
+                const int colbase = n_blk * BLOCK_N + half * NCH * 32;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    uint8_t* box = boxes + c * 2048 + lane * 64;
+                    const float4* gp = reinterpret_cast<const float4*>(gamma + colbase + c * 32);
+                    const float4* bp = reinterpret_cast<const float4*>(beta + colbase + c * 32);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        uint4* slot = reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4));
+                        const uint4 rv = *slot;
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                        uint4 ov;
+                        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const float4 g4 = __ldg(gp + 2 * j4 + u), b4 = __ldg(bp + 2 * j4 + u);
+                            const float2 v0 = __half22float2(rh[2 * u]), v1 = __half22float2(rh[2 * u + 1]);
+                            oh[2 * u] = __floats2half2_rn((v0.x - mean) * rstd * g4.x + b4.x, (v0.y - mean) * rstd * g4.y + b4.y);
+                            oh[2 * u + 1] = __floats2half2_rn((v1.x - mean) * rstd * g4.z + b4.z, (v1.y - mean) * rstd * g4.w + b4.w);
+                        }
+                        *slot = ov;
+                    }
+                    ptx::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmap_c, boxes + c * 2048, colbase + c * 32, row0);
+                        ptx::bulk_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) ptx::bulk_wait_all();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -420,6 +666,42 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
         set_error("gemm_f16 launch: %s", cudaGetErrorString(e));
         return false;
     }
+    return true;
+}
+
+// x_out[M, 384] = LayerNorm(A[M, K] . W[384, K]^T + bias + residual) * gamma + beta  (gemm_f16_ln_kernel)
+bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
+                     const __half* residual, const float* gamma, const float* beta, float eps, __half* C, int M, int N, int K,
+                     int num_sms) {
+    if (M <= 0) return true;
+    if (N != 2 * GEMM_BLOCK_N || K % BLOCK_K != 0 || K <= 0 || !residual || !gamma || !beta) {
+        set_error("gemm_f16_res_ln: unsupported shape M=%d N=%d K=%d (N must be %d)", M, N, K, 2 * GEMM_BLOCK_N);
+        return false;
+    }
+    constexpr int LN_STAGES = 3;
+    using L = GemmLnSmem<GEMM_BLOCK_N, LN_STAGES>;
+    CUtensorMap ta, tb_local, tc, tr;
+    if (!make_tmap_f16_2d(&ta, A, (uint64_t)M, (uint64_t)K, BLOCK_M, BLOCK_K)) return false;
+    if (!make_tmap_f16_2d(&tc, C, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
+    if (!make_tmap_f16_2d(&tr, residual, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
+    if (!tmap_w) {
+        if (!make_tmap_f16_2d(&tb_local, W, (uint64_t)N, (uint64_t)K, GEMM_BLOCK_N, BLOCK_K)) return false;
+        tmap_w = &tb_local;
+    }
+    auto kern = gemm_f16_ln_kernel<GEMM_BLOCK_N, LN_STAGES>;
+    static thread_local int attr_dev_mask[8] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 256 || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) { set_error("gemm_f16_res_ln: %s", cudaGetErrorString(e)); return false; }
+        if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
+    }
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    const int grid = num_m < num_sms ? num_m : num_sms;
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("gemm_f16_res_ln launch: %s", cudaGetErrorString(e)); return false; }
     return true;
 }
 

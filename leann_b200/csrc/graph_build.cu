@@ -242,12 +242,23 @@ build_insert_search_kernel(const BuildArgs a) {
             warp_dists(q_s, a, nw_id, nw_d, nnew, lane);
             for (int i = 0; i < nnew; i++) list_insert(l_id, l_d, sz, a.ef, nw_id[i], nw_d[i], lane);
         }
+        // results: ascending, without the point itself (it is in the list when it already lives in the graph: repair sweeps)
         int* oi = a.out_ids + pi * a.ef;
         float* od = a.out_dist + pi * a.ef;
-        for (int i = lane; i < a.ef; i += 32) {
-            oi[i] = (i < sz) ? (l_id[i] & ~EXPANDED) : -1;
-            od[i] = (i < sz) ? l_d[i] : FLT_MAX;
+        int wr = 0;
+        for (int b0 = 0; b0 < sz; b0 += 32) {
+            const int i = b0 + lane;
+            const int id = (i < sz) ? (l_id[i] & ~EXPANDED) : me;
+            const bool keep = id != me;
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int o = wr + __popc(m & ((1u << lane) - 1));
+                oi[o] = id;
+                od[o] = l_d[i];
+            }
+            wr += __popc(m);
         }
+        for (int i = wr + lane; i < a.ef; i += 32) { oi[i] = -1; od[i] = FLT_MAX; }
         __syncwarp();
     }
 }

@@ -149,7 +149,13 @@ class TopicModel:
         sub_vocab = min(sub_vocab, nwords)
         topic_words = min(topic_words, sub_vocab)
         self.sub_vocab, self.tw = sub_vocab, topic_words
-        self.n_super = max(2, int(round(np.sqrt(n_topics))))
+        # super-topics: sqrt(T) of them up to one million passages (T = 31 250 topics -> 177 super-topics of ~5 600 passages);
+        # beyond that the super-topic SIZE is held there (T / 176.8), like the topic size, so that a passage's neighbourhood —
+        # ~32 in-topic passages, then ~5 600 weakly related ones — does not change with the corpus size.  With sqrt(T) at
+        # 10 M passages (18 000 per super-topic) the share of a query's exact top-10 inside its topic falls from 0.90 to
+        # 0.85 and no graph reaches recall@10 0.9 at efSearch 64 (0.84 / 0.88 / 0.91 at ef 64 / 96 / 128,
+        # profiles/r02_graph_recall_10m_sqrt_corpus.log).
+        self.n_super = max(2, int(round(np.sqrt(n_topics)))) if n_topics <= 31250 else int(round(n_topics / 176.8))
         self.super_words = (np.stack([rng.choice(nwords, sub_vocab, replace=False) for _ in range(self.n_super)])
                             .astype(np.int32) + FIRST_WORD_ID)                       # [S, sub_vocab]
         self.topic_super = rng.integers(0, self.n_super, n_topics).astype(np.int32)  # [T]

@@ -36,6 +36,15 @@ for (N, K, epi, name) in [(1152, 384, 0, "qkv"), (384, 384, 2, "attn-out+res"), 
     print(f"gemm {name:14s} M={T} N={N} K={K}: {dt*1e3:8.3f} ms  {2.0*T*N*K/dt/1e12:7.1f} TFLOP/s   (torch.matmul fp16 no epilogue: {2.0*T*N*K/t2/1e12:7.1f})")
     del A, W, res, C
 
+for K, name in ((384, "attn-out+res+LN fused"), (1536, "ffn-down+res+LN fused")):
+    N = 384
+    A = (torch.randn(T, K, device=dev) * 0.5).half(); W = (torch.randn(N, K, device=dev) * 0.05).half()
+    b = torch.randn(N, device=dev) * 0.1; res = torch.randn(T, N, device=dev).half(); gm = torch.ones(N, device=dev); bt = torch.zeros(N, device=dev)
+    C = torch.empty(T, N, device=dev, dtype=torch.float16)
+    dt = timeit(lambda: lib.lb2_test_gemm_res_ln_f16(A.data_ptr(), W.data_ptr(), b.data_ptr(), res.data_ptr(), gm.data_ptr(), bt.data_ptr(), 1e-12, C.data_ptr(), T, N, K))
+    print(f"gemm {name:22s} M={T} N={N} K={K}: {dt*1e3:8.3f} ms  {2.0*T*N*K/dt/1e12:7.1f} TFLOP/s")
+    del A, W, res, C
+
 H, heads = 384, 12
 for L in (64, 128, 256):
     n_seq = T // L

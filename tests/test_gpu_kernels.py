@@ -96,3 +96,30 @@ def test_attention_vs_torch(lib, cuda_ok, H, heads):
         worst = max(worst, (ctx[off:off + L].float() - ref).abs().max().item())
         off += L
     assert worst <= 4e-3, worst  # P is rounded to fp16 before P.V, output to fp16
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 1000, 148 * 128 + 77, 40000])
+@pytest.mark.parametrize("K", [384, 1536])
+def test_gemm_res_ln_fused_vs_torch(lib, cuda_ok, M, K):
+    """Linear + residual + LayerNorm in one kernel (gemm_f16_ln_kernel) against torch fp32 of the same op, with the
+    statistics real checkpoints have: LayerNorm gains up to 5, an outlier channel in the residual stream."""
+    N = 384
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    res = torch.randn(M, N, device="cuda", generator=g)
+    res[:, 7] *= 30.0
+    res = res.half()
+    gam = torch.exp(torch.randn(N, device="cuda", generator=g) * 0.5).clamp(0.3, 5.0)
+    bet = torch.randn(N, device="cuda", generator=g) * 0.3
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    rc = lib.lb2_test_gemm_res_ln_f16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), res.data_ptr(), gam.data_ptr(), bet.data_ptr(),
+                                      1e-12, C.data_ptr(), M, N, K)
+    assert rc == 0, lib.lb2_last_error()
+    y = (A.float() @ W.float().T + bias + res.float()).half().float()  # the pipeline normalises the fp16-rounded tensor
+    ref = torch.nn.functional.layer_norm(y, (N,), gam, bet, 1e-12)
+    assert torch.isfinite(C).all()
+    err = (C.float() - ref).abs()
+    tol = 4e-3 + 2e-3 * ref.abs()  # fp16 output rounding + an fp16 ulp of the pre-norm value flipping under accumulation-order noise
+    assert (err <= tol).all(), f"max err {err.max().item()} at {torch.nonzero(err > tol)[:3].tolist()}"
