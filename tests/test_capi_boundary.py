@@ -41,7 +41,7 @@ def test_struct_layouts_match_header(lib):
     from leann_b200 import capi
     assert ctypes.sizeof(capi.SearchParams) == 32
     assert ctypes.sizeof(capi.EncoderConfig) == 40
-    assert ctypes.sizeof(capi.SearchStats) == 7 * 8 + 6 * 8
+    assert ctypes.sizeof(capi.SearchStats) == 7 * 8 + 6 * 8 + 8  # + n_encoder_passes
     assert ctypes.sizeof(capi.IndexInfo) == 56
     p = capi.SearchParams()
     lib.lb2_default_params(ctypes.byref(p))
