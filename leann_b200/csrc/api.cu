@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -347,14 +348,25 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     tp.batch_size = std::max(0, P.batch_size);
     tp.check_rel = P.check_relative_distance != 0;
     const int deg0 = std::max(1, x->g.maxdeg0);
-    tp.cap_new = std::max(std::max(1, x->g.maxdeg_up), tp.batch_size > 0 ? tp.batch_size + deg0 : tp.beam * deg0);
-    tp.p2 = next_pow2(tp.cap_new);
     // PQ-guided pruning: like the reference, only when PQ data was loaded AND the parameters ask for it
     // (perform_pq_pruning, HNSW_search.cpp:442-445); otherwise the three knobs are ignored
     tp.pq_ratio = 1.0f - P.pq_pruning_ratio;
     tp.pq_mode = 0;
     if (x->dpq_codes && (tp.pq_ratio < 1.f || P.local_prune || P.send_neigh_times_ratio != 0.f))
         tp.pq_mode = P.local_prune ? 2 : (P.send_neigh_times_ratio > 1e-6f ? 3 : 1);
+    // unvisited neighbours one hop can gather.  Batch mode pops until total_neighbors >= batch_size, and with pruning each
+    // pop only counts pq_select_ratio of its neighbours (:567-568): up to batch_size / ratio (+ one row), never more than
+    // every candidate's row
+    int64_t gather = (int64_t)tp.beam * deg0;
+    if (tp.batch_size > 0) {
+        const int64_t all_rows = (int64_t)tp.hcap * deg0;
+        gather = tp.batch_size;
+        if (tp.pq_mode && tp.pq_ratio < 1.f)
+            gather = tp.pq_ratio > 0.f ? (int64_t)std::min<double>(std::ceil(tp.batch_size / (double)tp.pq_ratio) + 1, (double)all_rows) : all_rows;
+        gather = std::min(gather, all_rows) + deg0;
+    }
+    tp.cap_new = (int)std::max<int64_t>(std::max(1, x->g.maxdeg_up), gather);
+    tp.p2 = next_pow2(tp.cap_new);
     // a hop selects at most (new neighbours) + (growth of the examined share of the queue) + 1 nodes: <= 2 cap_new + 2
     tp.cap_req = tp.pq_mode ? 2 * tp.cap_new + 2 : tp.cap_new;
 

@@ -12,7 +12,7 @@
 //                   rounded up to 16 (<= 256).  Then O[128, 32] = P . V : Lp / 16 tcgen05.mma with A = P read from
 //                   TENSOR MEMORY and B = the v tile as an MN-major operand (rows = keys, no transpose needed).
 //   warps 0..3    : softmax, one thread per query row (tcgen05.ld 32x32b: TMEM lane = row, no shuffles): pass 1
-//                   row maximum, pass 2 p = 2^((s - m) * scale * log2 e) (ex2.approx.f16x2), row sum, fp16 P written back to TMEM
+//                   row maximum, pass 2 p = 2^((s - m) * scale * log2 e), row sum, fp16 P written back to TMEM
 //                   IN PLACE over the columns of S already consumed (tcgen05.st), zeros for keys >= L.  After the
 //                   P.V MMAs: O from TMEM -> * 1/sum -> fp16 -> ctx[token][h * 32 ..] (64 B per row).
 // TMEM columns of a CTA: S = [0, Lp) fp32, P = [0, Lp / 2) packed fp16 (aliases S), two O accumulators [192, 224) and
@@ -248,26 +248,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             // pass 2: probabilities (fp16, back into TMEM over the consumed S columns), row sum
             const float ms = m * scale_log2;
             float sum = 0.f;
-            // p = 2^x on the packed half-precision MUFU path (ex2.approx.ftz.f16x2: two exponentials per MUFU op — the fp32
-            // MUFU rate is what bounded this kernel): x = s * c - m * c <= 0 is formed in fp32, rounded to fp16 (absolute error
-            // <= 2^-11 |x|, i.e. a relative error of p that only matters where p is already ~0), and the result IS the fp16
-            // probability the P.V MMA consumes.  The row sum adds the same rounded values in fp32.
             auto exp_chunk = [&](int c, const uint32_t (&r)[32]) {
                 uint32_t pk[16];
-                const bool full = c * 32 + 32 <= L;
+                if (c * 32 + 32 <= L) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const float x0 = fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms);
-                    const float x1 = fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms);
-                    __half2 p = h2exp2(__floats2half2_rn(x0, x1));
-                    if (!full) {
-                        const __half2 keep = __halves2half2(c * 32 + 2 * j < L ? __float2half(1.f) : __float2half(0.f),
-                                                            c * 32 + 2 * j + 1 < L ? __float2half(1.f) : __float2half(0.f));
-                        p = __hmul2(p, keep);
+                    for (int j = 0; j < 16; j++) {
+                        const float p0 = ex2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms));
+                        const float p1 = ex2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms));
+                        sum += p0 + p1;
+                        pk[j] = pack2(p0, p1);
                     }
-                    const float2 pf = __half22float2(p);
-                    sum += pf.x + pf.y;
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&p);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        float p0 = ex2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms));
+                        float p1 = ex2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms));
+                        p0 = (c * 32 + 2 * j < L) ? p0 : 0.f;
+                        p1 = (c * 32 + 2 * j + 1 < L) ? p1 : 0.f;
+                        sum += p0 + p1;
+                        pk[j] = pack2(p0, p1);
+                    }
                 }
                 ptx::tmem_st_32x16(taddr + c * 16, pk);
             };
