@@ -455,6 +455,10 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     int kerr = 0;
     cudaMemcpy(&kerr, s.error, sizeof(int), cudaMemcpyDeviceToHost);
+    if (kerr == 3) {  // the reference's fetch raises on NaN embeddings (HNSW_zmq.cpp:383-400)
+        set_error("a passage embedding or stored vector contains NaN");
+        return LB2_ERR_STATE;
+    }
     if (kerr) {
         set_error("PQ-guided pruning: a query exceeded %d PQ candidates (raise it with lb2_set_option(\"pq_queue_cap\"))", x->pq_cap);
         return LB2_ERR_STATE;
