@@ -361,8 +361,8 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     if (tp.batch_size > 0) {
         const int64_t all_rows = (int64_t)tp.hcap * deg0;
         gather = tp.batch_size;
-        if (tp.pq_mode && tp.pq_ratio < 1.f)
-            gather = tp.pq_ratio > 0.f ? (int64_t)std::min<double>(std::ceil(tp.batch_size / (double)tp.pq_ratio) + 1, (double)all_rows) : all_rows;
+        if (tp.pq_mode && tp.pq_ratio < 1.f)  // every pop also truncates its contribution to an int: up to one lost per pop
+            gather = tp.pq_ratio > 0.f ? (int64_t)std::min<double>(std::ceil((tp.batch_size + tp.hcap) / (double)tp.pq_ratio) + 1, (double)all_rows) : all_rows;
         gather = std::min(gather, all_rows) + deg0;
     }
     tp.cap_new = (int)std::max<int64_t>(std::max(1, x->g.maxdeg_up), gather);
@@ -455,6 +455,14 @@ int search_impl(lb2_index* x, int64_t nq, const float* d_q, int64_t k, float* d_
     if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return LB2_ERR_CUDA; }
     int kerr = 0;
     cudaMemcpy(&kerr, s.error, sizeof(int), cudaMemcpyDeviceToHost);
+    if (kerr == 4) {
+        set_error("batch_size with PQ pruning gathered more neighbours in one hop than this build reserves shared memory for");
+        return LB2_ERR_STATE;
+    }
+    if (kerr == 3) {  // the reference's fetch raises on NaN embeddings (HNSW_zmq.cpp:383-400)
+        set_error("a passage embedding or stored vector contains NaN");
+        return LB2_ERR_STATE;
+    }
     if (kerr) {
         set_error("PQ-guided pruning: a query exceeded %d PQ candidates (raise it with lb2_set_option(\"pq_queue_cap\"))", x->pq_cap);
         return LB2_ERR_STATE;

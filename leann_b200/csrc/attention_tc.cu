@@ -53,14 +53,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// work list: one entry per (passage, 128-row query block); a passage's blocks are adjacent
-__global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_len, int n_seq, int* __restrict__ items,
-                                          int* __restrict__ count) {
+// work list: one descriptor per (passage, 128-row query block): {first packed row of the passage, length, query block, passage}.
+// One 16-byte load per work item in the kernel (no dependent items -> seq_len -> seq_start chain); a passage's blocks are adjacent.
+__global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len, int n_seq,
+                                          int row_base, int4* __restrict__ desc, int* __restrict__ count) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seq) return;
-    const int nb = (seq_len[s] + ATC_TM - 1) / ATC_TM;
+    const int L = seq_len[s];
+    const int nb = (L + ATC_TM - 1) / ATC_TM;
     const int base = atomicAdd(count, nb);
-    for (int i = 0; i < nb; i++) items[base + i] = s * 8 + i;
+    for (int i = 0; i < nb; i++) desc[base + i] = make_int4(seq_start[s] - row_base, L, i, s);
 }
 
 // Pipeline of one CTA over its items i = 0, 1, ... (two CTAs per SM interleave):
@@ -71,8 +73,7 @@ __global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_len, i
 // A long item (S wider than 192 columns) would overwrite the O accumulators: both sides drain the pending read-outs first.
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
-                    const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
-                    const int* __restrict__ items, const int* __restrict__ n_items, int row_base, int heads, int hidden,
+                    const int4* __restrict__ desc, const int* __restrict__ n_items, int heads, int hidden,
                     __half* __restrict__ ctx) {
     extern __shared__ uint8_t att_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -114,15 +115,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
 
     if (warp == 4) {
         if (lane == 0) {
-            // ===== TMA producer
+            // ===== TMA producer (the descriptor of the next item is fetched while this one's loads are issued)
+            int4 cur = n_it > 0 ? __ldg(&desc[blockIdx.x / heads]) : make_int4(0, 0, 0, 0);
             for (int it = 0; it < n_it; it++) {
                 const int w = blockIdx.x + it * gridDim.x;
+                const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;
                 const int stage = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
-                const int item = items[w / heads], h = w % heads;
-                const int s = item >> 3;
-                const int L = seq_len[s];
-                const int row0 = seq_start[s] - row_base;
+                const int h = w % heads;
+                const int L = cur.y;
+                const int row0 = cur.x;
                 const int nbox = (L + ATC_BOX - 1) / ATC_BOX;
                 ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
                 uint8_t* qk = smem + stage * ATC_STAGE_BYTES;
@@ -132,29 +134,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                     ptx::tma_load_3d(qk + b * ATC_BOX * 128, &tmap_qk, &full_bar[stage], 0, row0 + b * ATC_BOX, h);
                     ptx::tma_load_3d(v + b * ATC_BOX * 64, &tmap_v, &full_bar[stage], 2 * ATC_HD, row0 + b * ATC_BOX, h);
                 }
+                cur = nxt;
             }
         }
     } else if (warp == 5) {
         if (lane == 0 && n_it > 0) {
             // ===== MMA issuer
-            auto issue_s = [&](int it) {
-                const int item = items[(blockIdx.x + it * gridDim.x) / heads];
-                const int qb = item & 7;
-                const int Lp = (seq_len[item >> 3] + 15) & ~15;
+            auto issue_s = [&](int it, const int4& d) {
+                const int Lp = (d.y + 15) & ~15;
                 const uint32_t qk = ptx::smem_u32(smem + (it & 1) * ATC_STAGE_BYTES);
-                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + qb * ATC_TM * 128);
+                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + d.z * ATC_TM * 128);
                 const uint64_t b_desc = ptx::make_sw128_kmajor_desc(qk) + 4;  // the k half of the (q | k) rows: +64 B
                 const uint32_t idesc_s = ptx::make_idesc_f16(ATC_TM, Lp);
 #pragma unroll
                 for (int k = 0; k < ATC_HD / 16; k++) ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0);
                 ptx::umma_commit(s_ready);
             };
+            int4 cur = __ldg(&desc[blockIdx.x / heads]);
+            int4 nxt = n_it > 1 ? __ldg(&desc[(blockIdx.x + gridDim.x) / heads]) : cur;
             ptx::mbar_wait(&full_bar[0], 0);
             ptx::tc_fence_after();
-            issue_s(0);
+            issue_s(0, cur);
             for (int it = 0; it < n_it; it++) {
                 const int stage = it & 1, b = it & 1;
-                const int Lp = (seq_len[items[(blockIdx.x + it * gridDim.x) / heads] >> 3] + 15) & ~15;
+                const int Lp = (cur.y + 15) & ~15;
+                const int4 nn = it + 2 < n_it ? __ldg(&desc[(blockIdx.x + (it + 2) * gridDim.x) / heads]) : nxt;
                 ptx::mbar_wait(p_ready, it & 1);
                 ptx::mbar_wait(&o_free[b], ((it >> 1) & 1) ^ 1);  // the previous user of this O accumulator has been read out
                 ptx::tc_fence_after();
@@ -166,15 +170,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 ptx::umma_commit(&o_ready[b]);
                 ptx::umma_commit(&empty_bar[stage]);
                 if (it + 1 < n_it) {
-                    const int Ln = seq_len[items[(blockIdx.x + (it + 1) * gridDim.x) / heads] >> 3];
                     ptx::mbar_wait(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1);
-                    if (((Ln + 15) & ~15) > ATC_LONG) {  // S(it + 1) covers the O accumulators: O(it) and O(it - 1) must be out
+                    if (((nxt.y + 15) & ~15) > ATC_LONG) {  // S(it + 1) covers the O accumulators: O(it) and O(it - 1) must be out
                         ptx::mbar_wait(&o_free[b], (it >> 1) & 1);
                         if (it >= 1) ptx::mbar_wait(&o_free[b ^ 1], ((it - 1) >> 1) & 1);
                     }
                     ptx::tc_fence_after();
-                    issue_s(it + 1);
+                    issue_s(it + 1, nxt);
                 }
+                cur = nxt;
+                nxt = nn;
             }
         }
     } else {
@@ -211,11 +216,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             }
         };
 
+        int4 cur = n_it > 0 ? __ldg(&desc[blockIdx.x / heads]) : make_int4(0, 0, 0, 0);
         for (int it = 0; it < n_it; it++) {
             const int w = blockIdx.x + it * gridDim.x;
-            const int item = items[w / heads], h = w % heads;
-            const int s = item >> 3, qb = item & 7;
-            const int L = seq_len[s];
+            const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;  // in flight during this item's softmax
+            const int h = w % heads;
+            const int qb = cur.z;
+            const int L = cur.y;
             const int q = qb * ATC_TM + threadIdx.x;
             const int nch = (L + 31) >> 5;
             if (((L + 15) & ~15) > ATC_LONG)  // the MMA warp waits for these before it may issue S(it)
@@ -287,9 +294,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
             const float inv = 1.0f / sum;
-            const long long off = q < L ? static_cast<long long>(seq_start[s] - row_base + q) * hidden + h * ATC_HD : -1;
+            const long long off = q < L ? static_cast<long long>(cur.x + q) * hidden + h * ATC_HD : -1;
             if (it & 1) { inv_sum[1] = inv; out_off[1] = off; } else { inv_sum[0] = inv; out_off[0] = off; }
             while (pend < it) readout(pend++);  // O(it - 1): its P.V was issued long ago; runs while P.V(it) and S(it + 1) execute
+            cur = nxt;
         }
         while (pend < n_it) readout(pend++);
     }
@@ -311,9 +319,10 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
                          int* item_count, int row_base, int n_seq, int n_tokens, int hidden, int heads, __half* ctx,
                          bool build_items, int num_sms) {
     if (n_seq <= 0) return true;
+    int4* desc = reinterpret_cast<int4*>(items);  // 2 descriptors per passage at most: fits the [n_seq * 8] int work-list buffer
     if (build_items) {  // once per encoder pass: the list is the same for every layer
         LB2_CUDA_OK(cudaMemsetAsync(item_count, 0, sizeof(int), s));
-        attention_tc_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_len, n_seq, items, item_count);
+        attention_tc_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_start, seq_len, n_seq, row_base, desc, item_count);
         LB2_CUDA_OK(cudaGetLastError());
     }
     CUtensorMap tm_qk, tm_v;
@@ -327,8 +336,7 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
         LB2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
-    attention_tc_kernel<<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, seq_start, seq_len, items, item_count, row_base,
-                                                                  heads, hidden, ctx);
+    attention_tc_kernel<<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx);
     LB2_CUDA_OK(cudaGetLastError());
     return true;
 }

@@ -371,7 +371,11 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
             for (int i = 0; i < n_req; i++) {
                 const int node = w.req[i];
                 const float* e = st.recompute ? st.E + (size_t)slot_rd[node] * d : st.vectors + (size_t)node * d;
-                const float dist = canon_dist(w.q, e, d, g.metric_ip, lane);
+                float dist = canon_dist(w.q, e, d, g.metric_ip, lane);
+                if (dist != dist) {  // NaN embedding: the reference raises (HNSW_zmq.cpp:383-400); flag it and keep the heaps sane
+                    if (lane == 0) atomicExch(st.error, 3);
+                    dist = FLT_MAX;
+                }
                 if (lane == 0) w.rq_dis[i] = dist;
             }
             __syncwarp();
@@ -531,6 +535,10 @@ hnsw_step_kernel(const DevGraph g, const TravParams p, const TravState st, int m
                         fresh = ((__ldcg(&vis[v1 >> 5]) >> (v1 & 31)) & 1u) == 0;  // L2 read: bits are set with atomics
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, fresh);
+                    if (nnew + __popc(m) > p.cap_new) {  // cannot happen for sizes derived in search_impl; never write past the buffer
+                        if (lane == 0) atomicExch(st.error, 4);
+                        break;
+                    }
                     if (fresh) w.rq[nnew + __popc(m & ((1u << lane) - 1))] = v1;
                     nnew += __popc(m);
                     cnt += __popc(m);
