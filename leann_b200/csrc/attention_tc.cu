@@ -193,14 +193,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
         auto readout = [&](int j) {
             const int b = j & 1;
             uint32_t o[32];
+            const long long off = b ? out_off[1] : out_off[0];
             ptx::mbar_wait(&o_ready[b], (j >> 1) & 1);
-            ptx::tc_fence_after();
-            ptx::tmem_ld_32x32(taddr + ATC_O_COL0 + 32 * b, o);
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
+            if (__any_sync(0xffffffffu, off >= 0)) {  // a warp whose 32 rows all lie beyond the passage has nothing to read
+                ptx::tc_fence_after();
+                ptx::tmem_ld_32x32(taddr + ATC_O_COL0 + 32 * b, o);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+            }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&o_free[b]);
-            const long long off = b ? out_off[1] : out_off[0];
             if (off >= 0) {
                 const float inv = b ? inv_sum[1] : inv_sum[0];
                 uint4* dst = reinterpret_cast<uint4*>(ctx + off);
@@ -228,6 +230,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             if (((L + 15) & ~15) > ATC_LONG)  // the MMA warp waits for these before it may issue S(it)
                 while (pend < it) readout(pend++);
             ptx::mbar_wait(s_ready, it & 1);
+            if (qb * ATC_TM + warp * 32 >= L) {
+                // all 32 rows of this warp lie beyond the passage (short passages, last query block): no TMEM traffic, no
+                // exponentials — only the barrier protocol (waiting on S keeps the warp from running a phase ahead)
+                if (lane == 0) ptx::mbar_arrive(p_ready);
+                if (it & 1) out_off[1] = -1; else out_off[0] = -1;
+                while (pend < it) readout(pend++);
+                cur = nxt;
+                continue;
+            }
             ptx::tc_fence_after();
             uint32_t ra[32], rb[32];
             // pass 1: row maximum over the L valid keys (TMEM loads one chunk ahead of the arithmetic)
