@@ -402,7 +402,8 @@ def upper_level_arrays(levels: np.ndarray, upper: dict, M: int, dev):
 @torch.no_grad()
 def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: int = 12345, device: str | None = None,
                                  ef_construction: int = 200, growth: float = 0.25, min_seed: int = 20000,
-                                 max_batch: int = 1 << 20, sweeps: int = 0, fill: int = 0, verbose: bool = False) -> CSRGraph:
+                                 max_batch: int = 1 << 20, sweeps: int = 0, fill: int = 0, cover: int = 0,
+                                 verbose: bool = False) -> CSRGraph:
     """HNSW construction the way the reference does it — every point is inserted by searching the graph built so far
     (hnsw_add_vertices, faiss/IndexHNSW.cpp:59-280: upper levels first, level-0-only points last) — run batch-parallel
     on the GPU: the points of a batch search concurrently (lb2_build_insert_search, one warp per point), select their
@@ -410,7 +411,8 @@ def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: i
     `growth` x the points already inserted, so a new point misses at most that share of its potential neighbours at
     insertion time; later insertions link back to it, and `sweeps` optional passes re-search every point on the finished
     graph to repair what the batches missed.  `fill` > 0 tops forward lists up to that many links with the nearest
-    rejected candidates (the reference's keep_max_size_level0 idea with a settable floor).  The upper levels (3 % of the points) and the level-0 seed among them are
+    rejected candidates (the reference's keep_max_size_level0 idea with a settable floor).  `cover` > 0 runs that many
+    rounds of level-1 coverage promotion after the level-0 graph is complete (see below).  The upper levels (3 % of the points) and the level-0 seed among them are
     built exactly (brute-force lists) by the batch builder above.  CUDA only."""
     from . import capi
 
@@ -506,5 +508,34 @@ def build_hnsw_graph_incremental(emb, M: int = 32, metric: str = "mips", seed: i
             isnew = (fi[:, :, None] != old[:, None, :]).all(2) & (fi >= 0)
             src = p64[:, None].expand_as(fi)[isnew]
             _merge_incoming(xs, sq, adj, adjd, fi[isnew].long(), src, fd[isnew], cap0, metric_ip)
+    if cover > 0 and max_level >= 1:
+        # Coverage of level 1.  Random level draws leave ~1/e of all neighbourhoods of ~M points without any member above
+        # level 0, and a query whose neighbourhood has no such member can only be reached through level-0 links.  Promote a
+        # spread-out subset of the uncovered points (no level >= 1 point in their own level-0 list; local minima by id, so
+        # promoted points are not adjacent) to level 1 and rebuild that level.  The format and the search are unchanged:
+        # levels are a free choice of the builder (the reference draws them at random, HNSW::random_level).
+        lv = torch.from_numpy(levels.astype(np.int32)).to(dev)
+        ids = torch.arange(n, device=dev)
+        for _ in range(cover):
+            up = lv > 1
+            nb_up = torch.zeros(n, dtype=torch.bool, device=dev)
+            for b0 in range(0, n, 1 << 20):
+                a = adj[b0:b0 + (1 << 20)].long()
+                nb_up[b0:b0 + (1 << 20)] = (up[a.clamp(min=0)] & (a >= 0)).any(1)
+            unc = ~(up | nb_up)
+            if not bool(unc.any()):
+                break
+            promote = torch.zeros(n, dtype=torch.bool, device=dev)
+            for b0 in range(0, n, 1 << 20):
+                a = adj[b0:b0 + (1 << 20)].long()
+                rows = ids[b0:b0 + (1 << 20)]
+                cand = torch.where((a >= 0) & unc[a.clamp(min=0)], a, torch.full_like(a, n))  # uncovered neighbours
+                promote[b0:b0 + (1 << 20)] = unc[rows] & (rows < cand.min(1).values)
+            lv = torch.where(promote, torch.full_like(lv, 2), lv)
+            if verbose:
+                print(f"  coverage round: {int(unc.sum())} uncovered points, {int(promote.sum())} promoted to level 1", flush=True)
+        levels = lv.cpu().numpy().astype(np.int32)
+        members = np.nonzero(levels > 1)[0]
+        upper[1] = (members.astype(np.int64), _build_level_exact(x, levels, members, 1, M, metric_ip))
     level0 = adj.cpu().numpy()
     return csr_from_padded(d, METRIC_INNER_PRODUCT if metric_ip else METRIC_L2, levels, level0, upper, entry, M=M)

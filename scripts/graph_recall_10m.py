@@ -37,7 +37,7 @@ for v in variants:
         k, _, val = kv.partition("=")
         kw[k] = float(val) if "." in val else int(val)
     t = time.time()
-    g = build_hnsw_graph_incremental(E, M=32, metric="mips", device="cuda:0", **kw)
+    g = build_hnsw_graph_incremental(E, M=32, metric="mips", device="cuda:0", verbose=bool(os.environ.get("LB2_BENCH_VERBOSE")), **kw)
     torch.cuda.synchronize(); bt = time.time() - t
     f = work / "g.index"; csr.write_compact_index(str(f), g)
     idx = capi.Index(str(f), 0); idx.set_vectors_device(E.data_ptr())
