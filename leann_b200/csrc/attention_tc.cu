@@ -126,7 +126,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 const int L = cur.y;
                 const int row0 = cur.x;
                 const int nbox = (L + ATC_BOX - 1) / ATC_BOX;
-                ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                ptx::mbar_wait_sleep(&empty_bar[stage], ph ^ 1, 256);
                 uint8_t* qk = smem + stage * ATC_STAGE_BYTES;
                 uint8_t* v = qk + ATC_QK_BYTES;
                 ptx::mbar_expect_tx(&full_bar[stage], nbox * ATC_BOX * (128 + 64));
@@ -152,15 +152,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             };
             int4 cur = __ldg(&desc[blockIdx.x / heads]);
             int4 nxt = n_it > 1 ? __ldg(&desc[(blockIdx.x + gridDim.x) / heads]) : cur;
-            ptx::mbar_wait(&full_bar[0], 0);
+            ptx::mbar_wait_sleep(&full_bar[0], 0, 64);
             ptx::tc_fence_after();
             issue_s(0, cur);
             for (int it = 0; it < n_it; it++) {
                 const int stage = it & 1, b = it & 1;
                 const int Lp = (cur.y + 15) & ~15;
                 const int4 nn = it + 2 < n_it ? __ldg(&desc[(blockIdx.x + (it + 2) * gridDim.x) / heads]) : nxt;
-                ptx::mbar_wait(p_ready, it & 1);
-                ptx::mbar_wait(&o_free[b], ((it >> 1) & 1) ^ 1);  // the previous user of this O accumulator has been read out
+                ptx::mbar_wait_sleep(p_ready, it & 1, 32);
+                ptx::mbar_wait_sleep(&o_free[b], ((it >> 1) & 1) ^ 1, 32);  // the previous user of this O accumulator has been read out
                 ptx::tc_fence_after();
                 const uint32_t vb = ptx::smem_u32(smem + stage * ATC_STAGE_BYTES) + ATC_QK_BYTES;
                 const uint32_t idesc_o = ptx::make_idesc_f16(ATC_TM, ATC_HD) | ptx::IDESC_B_MN_MAJOR;
@@ -170,10 +170,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 ptx::umma_commit(&o_ready[b]);
                 ptx::umma_commit(&empty_bar[stage]);
                 if (it + 1 < n_it) {
-                    ptx::mbar_wait(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                    ptx::mbar_wait_sleep(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1, 32);
                     if (((nxt.y + 15) & ~15) > ATC_LONG) {  // S(it + 1) covers the O accumulators: O(it) and O(it - 1) must be out
-                        ptx::mbar_wait(&o_free[b], (it >> 1) & 1);
-                        if (it >= 1) ptx::mbar_wait(&o_free[b ^ 1], ((it - 1) >> 1) & 1);
+                        ptx::mbar_wait_sleep(&o_free[b], (it >> 1) & 1, 32);
+                        if (it >= 1) ptx::mbar_wait_sleep(&o_free[b ^ 1], ((it - 1) >> 1) & 1, 32);
                     }
                     ptx::tc_fence_after();
                     issue_s(it + 1, nxt);
@@ -194,7 +194,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             const int b = j & 1;
             uint32_t o[32];
             const long long off = b ? out_off[1] : out_off[0];
-            ptx::mbar_wait(&o_ready[b], (j >> 1) & 1);
+            ptx::mbar_wait_sleep(&o_ready[b], (j >> 1) & 1, 32);
             if (__any_sync(0xffffffffu, off >= 0)) {  // a warp whose 32 rows all lie beyond the passage has nothing to read
                 ptx::tc_fence_after();
                 ptx::tmem_ld_32x32(taddr + ATC_O_COL0 + 32 * b, o);
@@ -229,7 +229,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             const int nch = (L + 31) >> 5;
             if (((L + 15) & ~15) > ATC_LONG)  // the MMA warp waits for these before it may issue S(it)
                 while (pend < it) readout(pend++);
-            ptx::mbar_wait(s_ready, it & 1);
+            ptx::mbar_wait_sleep(s_ready, it & 1, 32);
             if (qb * ATC_TM + warp * 32 >= L) {
                 // all 32 rows of this warp lie beyond the passage (short passages, last query block): no TMEM traffic, no
                 // exponentials — only the barrier protocol (waiting on S keeps the warp from running a phase ahead)
