@@ -17,6 +17,7 @@
 // between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
 // M is ragged (varlen-packed tokens): TMA zero-fills rows past M, stores are row-masked.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -63,7 +64,7 @@ template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                   const float* __restrict__ bias, int M, int N, int K, int c_group) {
+                   const float* __restrict__ bias, int M, int N, int K, int c_group, int wait_ns) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                             : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -121,7 +122,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
                 for (int kb = 0; kb < num_k; kb++) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
                     ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -191,7 +192,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         ptx::tma_load_2d(stage_buf + c * 2048, &tmap_r, &res_bar[ew], colbase + c * 32, row0);
                 }
             }
-            ptx::mbar_wait(&tmem_full[as], aphase);
+            ptx::mbar_wait_ns(&tmem_full[as], aphase, wait_ns);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + half * NCH * 32;
             uint32_t r[2][32];
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   int M, int K) {
+                   int M, int K, int wait_ns) {
     using L = GemmLnSmem<BLOCK_N, STAGES>;
     constexpr int N = 2 * BLOCK_N;
     constexpr int TMEM_COLS = 512;
@@ -354,7 +355,7 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x) {
                 for (int n_blk = 0; n_blk < 2; n_blk++) {
                     for (int kb = 0; kb < num_k; kb++) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
                         uint8_t* sa = smem + stage * L::STAGE_BYTES;
                         uint8_t* sb = sa + L::A_BYTES;
                         ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -421,7 +422,7 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             for (int n_blk = 0; n_blk < 2; n_blk++) {
                 uint8_t* boxes = smem + L::EPI_OFFSET + n_blk * L::TILE_BOX_BYTES + ew * NCH * 2048;
                 const int colbase = n_blk * BLOCK_N + half * NCH * 32;
-                ptx::mbar_wait(&tmem_full[n_blk], it & 1);
+                ptx::mbar_wait_ns(&tmem_full[n_blk], it & 1, wait_ns);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + n_blk * BLOCK_N + half * NCH * 32;
                 uint32_t r[2][32];
@@ -604,6 +605,12 @@ static bool make_tmap_f16_grouped(CUtensorMap* map, const void* ptr, uint64_t ro
     return true;
 }
 
+// sleep between mbarrier polls of the producer (x8) and the epilogue warps; 0 = spin.  LB2_GEMM_WAIT_NS overrides (A/B runs).
+static int gemm_wait_ns() {
+    static const int v = getenv("LB2_GEMM_WAIT_NS") ? atoi(getenv("LB2_GEMM_WAIT_NS")) : 0;
+    return v;
+}
+
 constexpr int GEMM_BLOCK_N = 192;
 constexpr int GEMM_STAGES = 4;
 
@@ -622,7 +629,7 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group, gemm_wait_ns());
     return cudaGetLastError();
 }
 
@@ -699,7 +706,7 @@ bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tm
     }
     const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
     const int grid = num_m < num_sms ? num_m : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("gemm_f16_res_ln launch: %s", cudaGetErrorString(e)); return false; }
     return true;

@@ -72,6 +72,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
+// ns == 0: plain spin (latency-critical waits)
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, unsigned ns) {
+    if (ns == 0) mbar_wait(bar, parity); else mbar_wait_sleep(bar, parity, ns);
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
