@@ -22,6 +22,8 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace lb2 {
@@ -74,7 +76,7 @@ __global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_start,
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
                     const int4* __restrict__ desc, const int* __restrict__ n_items, int heads, int hidden,
-                    __half* __restrict__ ctx) {
+                    __half* __restrict__ ctx, unsigned wait_ns, int skip_empty) {
     extern __shared__ uint8_t att_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ATC_BAR_OFFSET);
@@ -126,7 +128,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 const int L = cur.y;
                 const int row0 = cur.x;
                 const int nbox = (L + ATC_BOX - 1) / ATC_BOX;
-                ptx::mbar_wait_sleep(&empty_bar[stage], ph ^ 1, 256);
+                ptx::mbar_wait_ns(&empty_bar[stage], ph ^ 1, wait_ns);
                 uint8_t* qk = smem + stage * ATC_STAGE_BYTES;
                 uint8_t* v = qk + ATC_QK_BYTES;
                 ptx::mbar_expect_tx(&full_bar[stage], nbox * ATC_BOX * (128 + 64));
@@ -152,15 +154,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             };
             int4 cur = __ldg(&desc[blockIdx.x / heads]);
             int4 nxt = n_it > 1 ? __ldg(&desc[(blockIdx.x + gridDim.x) / heads]) : cur;
-            ptx::mbar_wait_sleep(&full_bar[0], 0, 64);
+            ptx::mbar_wait_ns(&full_bar[0], 0, wait_ns);
             ptx::tc_fence_after();
             issue_s(0, cur);
             for (int it = 0; it < n_it; it++) {
                 const int stage = it & 1, b = it & 1;
                 const int Lp = (cur.y + 15) & ~15;
                 const int4 nn = it + 2 < n_it ? __ldg(&desc[(blockIdx.x + (it + 2) * gridDim.x) / heads]) : nxt;
-                ptx::mbar_wait_sleep(p_ready, it & 1, 32);
-                ptx::mbar_wait_sleep(&o_free[b], ((it >> 1) & 1) ^ 1, 32);  // the previous user of this O accumulator has been read out
+                ptx::mbar_wait_ns(p_ready, it & 1, wait_ns);
+                ptx::mbar_wait_ns(&o_free[b], ((it >> 1) & 1) ^ 1, wait_ns);  // the previous user of this O accumulator has been read out
                 ptx::tc_fence_after();
                 const uint32_t vb = ptx::smem_u32(smem + stage * ATC_STAGE_BYTES) + ATC_QK_BYTES;
                 const uint32_t idesc_o = ptx::make_idesc_f16(ATC_TM, ATC_HD) | ptx::IDESC_B_MN_MAJOR;
@@ -170,10 +172,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 ptx::umma_commit(&o_ready[b]);
                 ptx::umma_commit(&empty_bar[stage]);
                 if (it + 1 < n_it) {
-                    ptx::mbar_wait_sleep(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1, 32);
+                    ptx::mbar_wait_ns(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1, wait_ns);
                     if (((nxt.y + 15) & ~15) > ATC_LONG) {  // S(it + 1) covers the O accumulators: O(it) and O(it - 1) must be out
-                        ptx::mbar_wait_sleep(&o_free[b], (it >> 1) & 1, 32);
-                        if (it >= 1) ptx::mbar_wait_sleep(&o_free[b ^ 1], ((it - 1) >> 1) & 1, 32);
+                        ptx::mbar_wait_ns(&o_free[b], (it >> 1) & 1, wait_ns);
+                        if (it >= 1) ptx::mbar_wait_ns(&o_free[b ^ 1], ((it - 1) >> 1) & 1, wait_ns);
                     }
                     ptx::tc_fence_after();
                     issue_s(it + 1, nxt);
@@ -193,16 +195,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
         auto readout = [&](int j) {
             const int b = j & 1;
             uint32_t o[32];
-            const long long off = b ? out_off[1] : out_off[0];
-            ptx::mbar_wait_sleep(&o_ready[b], (j >> 1) & 1, 32);
-            if (__any_sync(0xffffffffu, off >= 0)) {  // a warp whose 32 rows all lie beyond the passage has nothing to read
-                ptx::tc_fence_after();
-                ptx::tmem_ld_32x32(taddr + ATC_O_COL0 + 32 * b, o);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before();
-            }
+            ptx::mbar_wait(&o_ready[b], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32(taddr + ATC_O_COL0 + 32 * b, o);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&o_free[b]);
+            const long long off = b ? out_off[1] : out_off[0];
             if (off >= 0) {
                 const float inv = b ? inv_sum[1] : inv_sum[0];
                 uint4* dst = reinterpret_cast<uint4*>(ctx + off);
@@ -226,19 +226,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             const int qb = cur.z;
             const int L = cur.y;
             const int q = qb * ATC_TM + threadIdx.x;
-            const int nch = (L + 31) >> 5;
+            // a warp whose 32 query rows all lie beyond the passage (short passages, second query block) runs zero key
+            // chunks: no exponentials, no P rows (its O rows are never stored) — only the barrier protocol
+            const int nch = (skip_empty && qb * ATC_TM + warp * 32 >= L) ? 0 : (L + 31) >> 5;
             if (((L + 15) & ~15) > ATC_LONG)  // the MMA warp waits for these before it may issue S(it)
                 while (pend < it) readout(pend++);
-            ptx::mbar_wait_sleep(s_ready, it & 1, 32);
-            if (qb * ATC_TM + warp * 32 >= L) {
-                // all 32 rows of this warp lie beyond the passage (short passages, last query block): no TMEM traffic, no
-                // exponentials — only the barrier protocol (waiting on S keeps the warp from running a phase ahead)
-                if (lane == 0) ptx::mbar_arrive(p_ready);
-                if (it & 1) out_off[1] = -1; else out_off[0] = -1;
-                while (pend < it) readout(pend++);
-                cur = nxt;
-                continue;
-            }
+            ptx::mbar_wait(s_ready, it & 1);
             ptx::tc_fence_after();
             uint32_t ra[32], rb[32];
             // pass 1: row maximum over the L valid keys (TMEM loads one chunk ahead of the arithmetic)
@@ -252,7 +245,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                     for (int j = 0; j < 32; j++) m = (c * 32 + j < L) ? fmaxf(m, __uint_as_float(r[j])) : m;
                 }
             };
-            ptx::tmem_ld_32x32(taddr, ra);
+            if (nch > 0) ptx::tmem_ld_32x32(taddr, ra);
             for (int c = 0; c < nch; c += 2) {
                 ptx::tmem_ld_wait();
                 if (c + 1 < nch) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
@@ -289,7 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 }
                 ptx::tmem_st_32x16(taddr + c * 16, pk);
             };
-            ptx::tmem_ld_32x32(taddr, ra);
+            if (nch > 0) ptx::tmem_ld_32x32(taddr, ra);
             for (int c = 0; c < nch; c += 2) {
                 ptx::tmem_ld_wait();
                 if (c + 1 < nch) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
@@ -347,7 +340,17 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
         LB2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
-    attention_tc_kernel<<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx);
+    // LB2_ATTN_WAIT_NS > 0: the TMA and MMA warps sleep that long between mbarrier polls instead of spinning (A/B switch)
+    static const unsigned wait_ns = [] {
+        const char* e = getenv("LB2_ATTN_WAIT_NS");
+        return e ? static_cast<unsigned>(atoi(e)) : 0u;
+    }();
+    static const int skip_empty = [] {
+        const char* e = getenv("LB2_ATTN_SKIP");
+        return e ? atoi(e) : 1;
+    }();
+    attention_tc_kernel<<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx, wait_ns,
+                                                                  skip_empty);
     LB2_CUDA_OK(cudaGetLastError());
     return true;
 }
