@@ -36,7 +36,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "QPS @ recall@10 (HNSW selective recompute, all-MiniLM-L6-v2 384d, efSearch=64, k=10)"
-WORLD_VERSION = "w3"  # bump when the corpus generator / graph builder changes what a cached world holds
+WORLD_VERSION = "w4"  # bump when the corpus generator / graph builder changes what a cached world holds
 K = 10
 
 
@@ -169,8 +169,7 @@ def build_world(args, wd: Path, device: int):
     t0 = time.time()
     weights = synth.synthetic_weights(preset, 0)
     blob = synth.pack_weights(preset, weights)
-    tm, corpus = synth.make_corpus(args.chunks, preset.vocab_size, seed=1234, max_len=preset.max_pos, device=f"cuda:{device}")
-    queries = synth.make_queries(tm, args.pool, seed=4321)
+    tm, corpus, queries = synth.make_bench_corpus(args.chunks, preset.vocab_size, preset.max_pos, f"cuda:{device}", args.pool)
     info["corpus_s"] = time.time() - t0
     log(f"corpus: {corpus.n} chunks, {corpus.tokens.size/1e6:.1f} M tokens, {tm.n_topics} topics ({info['corpus_s']:.1f}s)")
     # 1. passage embeddings with the GPU encoder (stub graph: the encoder needs an open index handle)
@@ -246,8 +245,15 @@ def load_world(wd: Path):
                 info=info, preset=synth.MINILM_L6)
 
 
+def synth_corpus_params():
+    from leann_b200 import synth
+    return synth.BENCH_CORPUS
+
+
 def workload_string(args, W, nq, extra=""):
-    return (f"{args.chunks} synthetic chunks (mean {W['info']['mean_len']:.0f} tokens), all-MiniLM-L6-v2 384d architecture with "
+    c = synth_corpus_params()
+    return (f"{args.chunks} synthetic chunks (mean {W['info']['mean_len']:.0f} tokens; topic model: {c['topic_size']} chunks/topic, "
+            f"{c['p_topic']:.2f}/{c['p_super']:.2f} topic/super-topic token share), all-MiniLM-L6-v2 384d architecture with "
             f"seeded synthetic weights, HNSW M=32 recompute ({W['info'].get('graph_builder', '?')}), efSearch={args.ef}, "
             f"beam_width={args.beam}, k={K}, {nq} queries/step/GPU{extra}")
 

@@ -17,8 +17,7 @@ def test_one_million_passages_stored_vector_search_is_bit_exact(lib, cuda_ok, tm
     n, nq, k = 1_000_000, 64, 10
     preset = synth.MINILM_L6
     blob = synth.pack_weights(preset, synth.synthetic_weights(preset, 0))
-    tm, corpus = synth.make_corpus(n, preset.vocab_size, seed=1234, max_len=preset.max_pos, device="cuda:0")
-    queries = synth.make_queries(tm, nq, seed=4321)
+    tm, corpus, queries = synth.make_bench_corpus(n, preset.vocab_size, preset.max_pos, "cuda:0", nq)
     stub = tmp_path / "stub.index"
     csr.write_compact_index(str(stub), stub_graph(n, preset.hidden))
     enc = capi.Index(str(stub), 0)
