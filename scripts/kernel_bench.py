@@ -56,6 +56,18 @@ for L in (64, 128, 256):
     fl = 4.0 * L * H * n_seq * L
     print(f"attention L={L:3d} n_seq={n_seq}: {dt*1e3:8.3f} ms  {fl/dt/1e12:7.1f} TFLOP/s  ({n_seq*L/dt/1e6:7.1f} Mtok/s)")
     del qkv, ctx
+# the bench corpus' length distribution: N(128, 48) clipped to [16, 256]
+gl = torch.Generator().manual_seed(1)
+lens = torch.clamp((torch.randn(T // 128, generator=gl) * 48 + 128).round(), 16, 256).to(torch.int32)
+Tm = int(lens.sum())
+qkv = (torch.randn(Tm, 3 * H, device=dev)).half()
+ctx = torch.empty(Tm, H, device=dev, dtype=torch.float16)
+dl = lens.to(dev)
+ds = (torch.cumsum(dl, 0) - dl).to(torch.int32)
+dt = timeit(lambda: lib.lb2_test_attention_f16(qkv.data_ptr(), ds.data_ptr(), dl.data_ptr(), len(lens), Tm, H, heads, 256, ctx.data_ptr()), 5)
+fl = 4.0 * H * float((lens.double() ** 2).sum())
+print(f"attention mixed lengths (mean {Tm/len(lens):.0f}) n_seq={len(lens)} tokens={Tm}: {dt*1e3:8.3f} ms  {fl/dt/1e12:7.1f} TFLOP/s  ({Tm/dt/1e6:7.1f} Mtok/s)")
+del qkv, ctx
 
 x = torch.randn(T, H, device=dev).half(); g = torch.randn(H, device=dev); bb = torch.randn(H, device=dev); o = torch.empty_like(x)
 dt = timeit(lambda: lib.lb2_test_layernorm_f16(x.data_ptr(), g.data_ptr(), bb.data_ptr(), o.data_ptr(), T, H, 1e-12))
