@@ -273,6 +273,248 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Weight-stationary variant for the K = 384 projections (QKV, FFN up).
+//
+// gemm_f16_tn_kernel refills shared memory with (128 + 192) rows x 128 B per 64-deep k-block, i.e. 40 KB per 384 tensor
+// clocks = 106 B/clk per SM; ncu shows the tensor pipe active 50-55 % of the time on these shapes with HBM at 35-40 % —
+// the L2 -> shared-memory fill rate, not HBM or the epilogue, is what the MMA warp waits for (cuBLAS lands on the same
+// ~950 TFLOP/s).  With K = 384 a whole 192-row panel of W is only 144 KB: this kernel keeps it resident in shared memory
+// and streams just the activations (16 KB per k-block = 43 B/clk).  The grid is (CTAs per panel) x (panels): CTA (i, p)
+// computes panel p of the i-th contiguous slice of row blocks, so the N / 192 CTAs that need the same rows of A read them at
+// the same time and all but the first read hit L2 (with 148 SMs and 6 or 8 panels, 144 CTAs run; a free-form split of the
+// tile list would use all 148 but skew the readers of a row block by tens of tiles — hundreds of MB of L2 traffic apart).
+// The kernel itself accepts any contiguous range of the panel-major tile list: a range that crosses a panel boundary
+// drains the MMAs that read the old panel (b_empty) and reloads.  Epilogue as in gemm_f16_tn_kernel (bias / GELU -> fp16
+// -> swizzled 32x32 box -> TMA store), one staging box per warp (reused per chunk: the box is free again long before the
+// next chunk's arithmetic is done), bias panel in shared memory.
+template <int BLOCK_N, int NUM_K, int STAGES>
+struct GemmWsSmem {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;       // one k-block of activations
+    static constexpr int B_SLAB = BLOCK_N * BLOCK_K * 2;        // one k-block of the weight panel
+    static constexpr int B_BYTES = NUM_K * B_SLAB;
+    static constexpr int A_OFFSET = B_BYTES;
+    static constexpr int EPI_OFFSET = A_OFFSET + STAGES * A_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * 2048;
+    static constexpr int BIAS_OFFSET = EPI_OFFSET + EPI_BYTES;
+    static constexpr int BAR_OFFSET = BIAS_OFFSET + BLOCK_N * 4;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 6) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+template <int BLOCK_N, int NUM_K, int STAGES, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, int M, int N, int c_group,
+                   int ctas_per_panel) {
+    using L = GemmWsSmem<BLOCK_N, NUM_K, STAGES>;
+    static_assert(L::TOTAL <= 232448, "shared memory budget");
+    static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU, "no residual variant");
+    constexpr int TMEM_COLS = 512;
+    static_assert(2 * BLOCK_N <= 512 && BLOCK_N % 64 == 0, "two accumulator stages must fit TMEM");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* b_full = tmem_empty + 2;
+    uint64_t* b_empty = b_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n = N / BLOCK_N;
+    // this CTA's contiguous range of the panel-major tile list (tile = panel * num_m + row block)
+    int t_begin, t_end;
+    if (ctas_per_panel > 0) {
+        const int panel = blockIdx.x / ctas_per_panel, idx = blockIdx.x - panel * ctas_per_panel;
+        t_begin = panel * num_m + static_cast<int>(static_cast<long long>(num_m) * idx / ctas_per_panel);
+        t_end = panel * num_m + static_cast<int>(static_cast<long long>(num_m) * (idx + 1) / ctas_per_panel);
+    } else {
+        const long long num_tiles = static_cast<long long>(num_m) * num_n;
+        t_begin = static_cast<int>(num_tiles * blockIdx.x / gridDim.x);
+        t_end = static_cast<int>(num_tiles * (blockIdx.x + 1) / gridDim.x);
+    }
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_c);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            ptx::mbar_init(&tmem_full[i], 1);
+            ptx::mbar_init(&tmem_empty[i], EPI_WARPS);
+        }
+        ptx::mbar_init(b_full, 1);
+        ptx::mbar_init(b_empty, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: the weight panel when it changes, the activation k-blocks always
+            int stage = 0;
+            uint32_t phase = 0, bphase = 0;
+            int cur_n = -1;
+            for (int tile = t_begin; tile < t_end; tile++) {
+                const int n_blk = tile / num_m, m_blk = tile - n_blk * num_m;
+                if (n_blk != cur_n) {
+                    if (cur_n >= 0) {  // every MMA that reads the old panel has retired
+                        ptx::mbar_wait(b_empty, bphase);
+                        bphase ^= 1;
+                    }
+                    ptx::mbar_expect_tx(b_full, L::B_BYTES);
+#pragma unroll
+                    for (int kb = 0; kb < NUM_K; kb++)
+                        ptx::tma_load_2d(smem + kb * L::B_SLAB, &tmap_b, b_full, kb * BLOCK_K, n_blk * BLOCK_N);
+                    cur_n = n_blk;
+                }
+                for (int kb = 0; kb < NUM_K; kb++) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], L::A_BYTES);
+                    ptx::tma_load_2d(smem + L::A_OFFSET + stage * L::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                                     m_blk * BLOCK_M);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer
+            constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0, bphase = 0;
+            int cur_n = -1;
+            int it = 0;
+            for (int tile = t_begin; tile < t_end; tile++, it++) {
+                const int n_blk = tile / num_m;
+                if (n_blk != cur_n) {
+                    ptx::mbar_wait(b_full, bphase);
+                    bphase ^= 1;
+                    cur_n = n_blk;
+                }
+                const int as = it & 1;
+                ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+#pragma unroll
+                for (int kb = 0; kb < NUM_K; kb++) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::A_OFFSET + stage * L::A_BYTES));
+                    const uint64_t b_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + kb * L::B_SLAB));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+                        ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full[as]);
+                if (tile + 1 < t_end && (tile + 1) / num_m != n_blk) ptx::umma_commit(b_empty);  // the panel may be replaced
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the tile's columns
+        const int quarter = warp & 3;
+        const int ew = warp - 4;
+        const int half = ew >> 2;
+        constexpr int NCH = BLOCK_N / 32 / 2;
+        uint8_t* box_base = smem + L::EPI_OFFSET + ew * 2048;
+        const int swz = (lane >> 1) & 3;
+        const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
+        int cur_n = -1;
+        int it = 0;
+        for (int tile = t_begin; tile < t_end; tile++, it++) {
+            const int n_blk = tile / num_m, m_blk = tile - n_blk * num_m;
+            if (n_blk != cur_n) {  // new panel: its bias slice into shared memory (all epilogue warps are past the old one)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < BLOCK_N) bias_s[et] = __ldg(bias + n_blk * BLOCK_N + et);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                cur_n = n_blk;
+            }
+            const int as = it & 1;
+            const int row0 = m_blk * BLOCK_M + quarter * 32;
+            const int colbase = n_blk * BLOCK_N + half * NCH * 32;
+            ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + half * NCH * 32;
+            uint32_t r[2][32];
+            ptx::tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                ptx::tmem_ld_wait();
+                if (c + 1 < NCH) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                const uint32_t(&acc)[32] = r[c & 1];
+                const int col0 = colbase + c * 32;
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + half * NCH * 32 + c * 32);
+                uint4 ov[4];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const float4 b4 = bp[2 * j4 + u];  // warp-uniform address: broadcast
+                        v[4 * u + 0] = __uint_as_float(acc[8 * j4 + 4 * u + 0]) + b4.x;
+                        v[4 * u + 1] = __uint_as_float(acc[8 * j4 + 4 * u + 1]) + b4.y;
+                        v[4 * u + 2] = __uint_as_float(acc[8 * j4 + 4 * u + 2]) + b4.z;
+                        v[4 * u + 3] = __uint_as_float(acc[8 * j4 + 4 * u + 3]) + b4.w;
+                    }
+                    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v[u] = gelu_fast(v[u]);
+                    }
+                    __half2* oh = reinterpret_cast<__half2*>(&ov[j4]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+                }
+                // the store issued from this warp's box one chunk ago must have finished reading it
+                if (lane == 0) ptx::bulk_wait_read<0>();
+                __syncwarp();
+                uint8_t* box = box_base + lane * 64;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) *reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4)) = ov[j4];
+                ptx::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (c_group > 0)
+                        ptx::tma_store_3d(&tmap_c, box_base, col0 % c_group, row0, col0 / c_group);
+                    else
+                        ptx::tma_store_2d(&tmap_c, box_base, col0, row0);
+                    ptx::bulk_commit();
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+        }
+        if (lane == 0) ptx::bulk_wait_all();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Residual projection with LayerNorm fused into the epilogue (hidden = 2 * BLOCK_N = 384 only):
 //     x_out = LayerNorm(A . W^T + bias + residual) * gamma + beta
 // i.e. the attention-output / FFN-down Linear, the residual add and BertSelfOutput / BertOutput's LayerNorm of one BERT
@@ -633,6 +875,41 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     return cudaGetLastError();
 }
 
+// weight-stationary kernel for K = 384 (LB2_GEMM_WS=0 falls back to the streaming kernel)
+constexpr int WS_NUM_K = 6;
+constexpr int WS_STAGES = 4;
+static bool gemm_ws_enabled() {
+    static const bool v = !(getenv("LB2_GEMM_WS") && atoi(getenv("LB2_GEMM_WS")) == 0);
+    return v;
+}
+
+template <int EPI>
+static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                                  const float* bias, int M, int N, int c_group, int num_sms) {
+    using L = GemmWsSmem<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES>;
+    auto kern = gemm_f16_ws_kernel<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES, EPI>;
+    static thread_local int attr_dev_mask[8] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 256 || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
+    }
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = N / GEMM_BLOCK_N;
+    int cpp = num_sms / num_n;  // CTAs per panel
+    if (cpp > num_m) cpp = num_m;
+    int grid = cpp * num_n;
+    const char* ff = getenv("LB2_GEMM_WS_FREEFORM");  // test hook: exercise the panel-change path
+    if (ff && atoi(ff) != 0) cpp = 0;
+    if (cpp == 0) {  // more panels than SMs: free-form split of the tile list
+        const long long tiles = static_cast<long long>(num_m) * num_n;
+        grid = tiles < num_sms ? static_cast<int>(tiles) : num_sms;
+    }
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N, c_group, cpp);
+    return cudaGetLastError();
+}
+
 // A [M,K] fp16 row-major, W [N,K] fp16 row-major (nn.Linear layout), C [M,N] fp16.
 // c_group > 0: C is written group-major, [N / c_group][M][c_group] (the per-head q|k|v layout attention reads).
 bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
@@ -663,6 +940,15 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
         tmap_w = &tb_local;
     }
     cudaError_t e;
+    if (K == WS_NUM_K * BLOCK_K && epi != EPI_BIAS_RES && gemm_ws_enabled()) {
+        e = epi == EPI_BIAS ? launch_gemm_ws<EPI_BIAS>(stream, ta, *tmap_w, tc, bias, M, N, c_group, num_sms)
+                            : launch_gemm_ws<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, bias, M, N, c_group, num_sms);
+        if (e != cudaSuccess) {
+            set_error("gemm_f16 (weight-stationary) launch: %s", cudaGetErrorString(e));
+            return false;
+        }
+        return true;
+    }
     switch (epi) {
         case EPI_BIAS: e = launch_gemm<EPI_BIAS>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
         case EPI_BIAS_GELU: e = launch_gemm<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, tr, bias, M, N, K, c_group, num_sms); break;
