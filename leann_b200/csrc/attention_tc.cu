@@ -116,41 +116,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 4) {
-        if (lane == 0) {
-            // ===== TMA producer (the descriptor of the next item is fetched while this one's loads are issued)
-            int4 cur = n_it > 0 ? __ldg(&desc[blockIdx.x / heads]) : make_int4(0, 0, 0, 0);
-            for (int it = 0; it < n_it; it++) {
-                const int w = blockIdx.x + it * gridDim.x;
-                const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;
-                const int stage = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                const int h = w % heads;
-                const int L = cur.y;
-                const int row0 = cur.x;
-                const int nbox = (L + ATC_BOX - 1) / ATC_BOX;
-                ptx::mbar_wait_ns(&empty_bar[stage], ph ^ 1, wait_ns);
-                uint8_t* qk = smem + stage * ATC_STAGE_BYTES;
-                uint8_t* v = qk + ATC_QK_BYTES;
+        // ===== TMA producer, whole warp + one elected issuer (the descriptor of the next item is fetched while this one's
+        // loads are issued)
+        int4 cur = n_it > 0 ? __ldg(&desc[blockIdx.x / heads]) : make_int4(0, 0, 0, 0);
+        for (int it = 0; it < n_it; it++) {
+            const int w = blockIdx.x + it * gridDim.x;
+            const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;
+            const int stage = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int h = w % heads;
+            const int L = cur.y;
+            const int row0 = cur.x;
+            const int nbox = (L + ATC_BOX - 1) / ATC_BOX;
+            ptx::mbar_wait_ns(&empty_bar[stage], ph ^ 1, wait_ns);
+            uint8_t* qk = smem + stage * ATC_STAGE_BYTES;
+            uint8_t* v = qk + ATC_QK_BYTES;
+            if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(&full_bar[stage], nbox * ATC_BOX * (128 + 64));
                 for (int b = 0; b < nbox; b++) {
                     ptx::tma_load_3d(qk + b * ATC_BOX * 128, &tmap_qk, &full_bar[stage], 0, row0 + b * ATC_BOX, h);
                     ptx::tma_load_3d(v + b * ATC_BOX * 64, &tmap_v, &full_bar[stage], 2 * ATC_HD, row0 + b * ATC_BOX, h);
                 }
-                cur = nxt;
             }
+            __syncwarp();
+            cur = nxt;
         }
     } else if (warp == 5) {
-        if (lane == 0 && n_it > 0) {
-            // ===== MMA issuer
+        if (n_it > 0) {
+            // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (warp-uniform control flow keeps the
+            // descriptors in uniform registers; under `if (lane == 0)` every tcgen05.mma sat in an ELECT / R2UR.BROADCAST
+            // loop and the ten small MMAs of an item cost more to issue than to execute)
             auto issue_s = [&](int it, const int4& d) {
                 const int Lp = (d.y + 15) & ~15;
                 const uint32_t qk = ptx::smem_u32(smem + (it & 1) * ATC_STAGE_BYTES);
                 const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + d.z * ATC_TM * 128);
                 const uint64_t b_desc = ptx::make_sw128_kmajor_desc(qk) + 4;  // the k half of the (q | k) rows: +64 B
                 const uint32_t idesc_s = ptx::make_idesc_f16(ATC_TM, Lp);
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < ATC_HD / 16; k++) ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0);
-                ptx::umma_commit(s_ready);
+                    for (int k = 0; k < ATC_HD / 16; k++)
+                        ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0);
+                    ptx::umma_commit(s_ready);
+                }
+                __syncwarp();
             };
             int4 cur = __ldg(&desc[blockIdx.x / heads]);
             int4 nxt = n_it > 1 ? __ldg(&desc[(blockIdx.x + gridDim.x) / heads]) : cur;
@@ -167,10 +175,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 const uint32_t vb = ptx::smem_u32(smem + stage * ATC_STAGE_BYTES) + ATC_QK_BYTES;
                 const uint32_t idesc_o = ptx::make_idesc_f16(ATC_TM, ATC_HD) | ptx::IDESC_B_MN_MAJOR;
                 const uint32_t o_tmem = tmem_base + ATC_O_COL0 + 32 * b;
-                for (int j = 0; j < Lp / 16; j++)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (1 KB) of V
-                    ptx::umma_f16_ts(o_tmem, tmem_base + 8 * j, ptx::make_mn_major_desc(vb + j * 1024, 64), idesc_o, j != 0);
-                ptx::umma_commit(&o_ready[b]);
-                ptx::umma_commit(&empty_bar[stage]);
+                if (ptx::elect_one()) {
+                    for (int j = 0; j < Lp / 16; j++)  // 16 keys per MMA: 8 TMEM columns of P, 16 rows (1 KB) of V
+                        ptx::umma_f16_ts(o_tmem, tmem_base + 8 * j, ptx::make_mn_major_desc(vb + j * 1024, 64), idesc_o, j != 0);
+                    ptx::umma_commit(&o_ready[b]);
+                    ptx::umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
                 if (it + 1 < n_it) {
                     ptx::mbar_wait_ns(&full_bar[(it + 1) & 1], ((it + 1) >> 1) & 1, wait_ns);
                     if (((nxt.y + 15) & ~15) > ATC_LONG) {  // S(it + 1) covers the O accumulators: O(it) and O(it - 1) must be out

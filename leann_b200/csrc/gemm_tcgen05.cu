@@ -115,52 +115,57 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / num_n, n_blk = tile % num_n;
-                for (int kb = 0; kb < num_k; kb++) {
-                    ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
-                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    uint8_t* sb = sa + L::A_BYTES;
+        // ===== TMA producer (whole warp, one elected issuer) =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            for (int kb = 0; kb < num_k; kb++) {
+                ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
+                uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                uint8_t* sb = sa + L::A_BYTES;
+                if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
                     ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+        // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform
+        // registers), one elected lane issues
+        constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        const uint32_t smem_base = ptx::smem_u32(smem);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < num_k; kb++) {
+                ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < num_k; kb++) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(sa);
-                    const uint64_t b_desc = ptx::make_sw128_kmajor_desc(sa + L::A_BYTES);
+                const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(sa);
+                const uint64_t b_desc = ptx::make_sw128_kmajor_desc(sa + L::A_BYTES);
+                if (ptx::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
                         // advance 16 fp16 = 32 B along K inside the 128B swizzle span: +2 in 16B units
                         ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     }
                     ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full[as]);  // accumulator complete
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (ptx::elect_one()) ptx::umma_commit(&tmem_full[as]);  // accumulator complete
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the tile's columns.
@@ -366,67 +371,80 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer: the weight panel when it changes, the activation k-blocks always
-            int stage = 0;
-            uint32_t phase = 0, bphase = 0;
-            int cur_n = -1;
-            for (int tile = t_begin; tile < t_end; tile++) {
-                const int n_blk = tile / num_m, m_blk = tile - n_blk * num_m;
-                if (n_blk != cur_n) {
-                    if (cur_n >= 0) {  // every MMA that reads the old panel has retired
-                        ptx::mbar_wait(b_empty, bphase);
-                        bphase ^= 1;
-                    }
+        // ===== TMA producer (whole warp, one elected issuer): the weight panel when it changes, the activation k-blocks always
+        int stage = 0;
+        uint32_t phase = 0, bphase = 0;
+        int cur_n = -1;
+        for (int tile = t_begin; tile < t_end; tile++) {
+            const int n_blk = tile / num_m, m_blk = tile - n_blk * num_m;
+            if (n_blk != cur_n) {
+                if (cur_n >= 0) {  // every MMA that reads the old panel has retired
+                    ptx::mbar_wait(b_empty, bphase);
+                    bphase ^= 1;
+                }
+                if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(b_full, L::B_BYTES);
 #pragma unroll
                     for (int kb = 0; kb < NUM_K; kb++)
                         ptx::tma_load_2d(smem + kb * L::B_SLAB, &tmap_b, b_full, kb * BLOCK_K, n_blk * BLOCK_N);
-                    cur_n = n_blk;
                 }
-                for (int kb = 0; kb < NUM_K; kb++) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                __syncwarp();
+                cur_n = n_blk;
+            }
+            for (int kb = 0; kb < NUM_K; kb++) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(&full_bar[stage], L::A_BYTES);
                     ptx::tma_load_2d(smem + L::A_OFFSET + stage * L::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K,
                                      m_blk * BLOCK_M);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer
-            constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0, bphase = 0;
-            int cur_n = -1;
-            int it = 0;
-            for (int tile = t_begin; tile < t_end; tile++, it++) {
-                const int n_blk = tile / num_m;
-                if (n_blk != cur_n) {
-                    ptx::mbar_wait(b_full, bphase);
-                    bphase ^= 1;
-                    cur_n = n_blk;
-                }
-                const int as = it & 1;
-                ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        // ===== MMA issuer.  The WHOLE warp runs the loop and one elected lane issues: with warp-uniform control flow the
+        // descriptors live in uniform registers; under `if (lane == 0)` the compiler wrapped every tcgen05.mma in an
+        // ELECT / R2UR.BROADCAST / BRA.U.ANY loop and the issuing thread, not the tensor pipe, set the pace
+        // (profiles/r02_gemm_ws_ncu.md).
+        constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0, bphase = 0;
+        int cur_n = -1;
+        int it = 0;
+        const uint32_t a_base = ptx::smem_u32(smem + L::A_OFFSET), b_base = ptx::smem_u32(smem);
+        for (int tile = t_begin; tile < t_end; tile++, it++) {
+            const int n_blk = tile / num_m;
+            if (n_blk != cur_n) {
+                ptx::mbar_wait(b_full, bphase);
+                bphase ^= 1;
+                cur_n = n_blk;
+            }
+            const int as = it & 1;
+            ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BLOCK_N;
 #pragma unroll
-                for (int kb = 0; kb < NUM_K; kb++) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::A_OFFSET + stage * L::A_BYTES));
-                    const uint64_t b_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + kb * L::B_SLAB));
+            for (int kb = 0; kb < NUM_K; kb++) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(a_base + stage * L::A_BYTES);
+                const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_base + kb * L::B_SLAB);
+                if (ptx::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; k++)
                         ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full[as]);
-                if (tile + 1 < t_end && (tile + 1) / num_m != n_blk) ptx::umma_commit(b_empty);  // the panel may be replaced
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            const bool panel_ends = tile + 1 < t_end && (tile + 1) / num_m != n_blk;  // the panel may be replaced
+            if (ptx::elect_one()) {
+                ptx::umma_commit(&tmem_full[as]);
+                if (panel_ends) ptx::umma_commit(b_empty);
+            }
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps, two per TMEM lane quarter, each owning half of the tile's columns
@@ -524,10 +542,10 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // 96 KB), accumulates per-row sum / sum of squares on the fp16-rounded values (the numerics of the unfused pipeline, which
 // normalised the fp16 tensor), exchanges them between the two warps that share a row, normalises in place and stores.
 // Same producer / MMA warps and mbarrier pipelines as gemm_f16_tn_kernel; 3 smem stages instead of 4 to make room.
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool PAIR>
 struct GemmLnSmem {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // a CTA pair splits the W rows of a panel
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_CHUNKS = BLOCK_N / 32 / 2;            // 32-column chunks per warp and half
     static constexpr int TILE_BOX_BYTES = EPI_WARPS * EPI_CHUNKS * 2048;
@@ -539,13 +557,24 @@ struct GemmLnSmem {
     static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16 + 1024;
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                   const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   int M, int K, int wait_ns) {
-    using L = GemmLnSmem<BLOCK_N, STAGES>;
+//
+// PAIR = true: two CTAs of a cluster work as one (tcgen05 cta_group::2, M = 256): each owns one 128-row block and loads
+// its own A tile plus HALF of the W rows of the panel (96 of 192); the MMA — issued by rank 0 only — reads both halves, each
+// CTA accumulates its rows in its own tensor memory and runs its own epilogue.  The shared-memory fill per CTA drops from
+// 40 KB to 28 KB per k-block (the MMA warp was waiting for it: tensor pipe 44-65 % active in the single-CTA kernels), and
+// the ring gets its fourth stage back.  Barriers: every CTA's TMA completes on rank 0's `full` barrier; `empty` and
+// `tmem_full` are multicast commits to both CTAs; all 16 epilogue warps of the pair arrive on rank 0's `tmem_empty`.
+template <int BLOCK_N, int STAGES, bool PAIR>
+__device__ __forceinline__ void
+gemm_f16_ln_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_c, const CUtensorMap& tmap_r,
+                 const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 int M, int K, int wait_ns) {
+    using L = GemmLnSmem<BLOCK_N, STAGES, PAIR>;
+    const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+    // row blocks are dealt to CTAs (pairs: to the pair, rank r takes the r-th of two consecutive ones; a block past the end
+    // is computed on zero-filled rows and stored nowhere)
+    const int blk_first = PAIR ? (blockIdx.x >> 1) * 2 + rank : blockIdx.x;
+    const int blk_step = gridDim.x;
     constexpr int N = 2 * BLOCK_N;
     constexpr int TMEM_COLS = 512;
     static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
@@ -576,45 +605,61 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], EPI_WARPS);
+            ptx::mbar_init(&tmem_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
         for (int i = 0; i < 2 * EPI_WARPS; i++) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (PAIR) {
+            ptx::tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();  // pair: the peer's barriers must be initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer: row block m, column halves 0 and 1 back to back
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x) {
-                for (int n_blk = 0; n_blk < 2; n_blk++) {
-                    for (int kb = 0; kb < num_k; kb++) {
-                        ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
-                        uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                        uint8_t* sb = sa + L::A_BYTES;
-                        ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        // ===== TMA producer (whole warp, one elected issuer): row block m, column halves 0 and 1 back to back
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int m_blk = blk_first; m_blk < num_m + rank; m_blk += blk_step) {
+            for (int n_blk = 0; n_blk < 2; n_blk++) {
+                for (int kb = 0; kb < num_k; kb++) {
+                    ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::A_BYTES;
+                    if (ptx::elect_one()) {
+                        if (PAIR) {
+                            // both CTAs' bytes complete on rank 0's barrier; rank 0 announces the total
+                            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                            ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                            ptx::tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K,
+                                                  n_blk * BLOCK_N + rank * (BLOCK_N / 2));
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer: half n accumulates in TMEM stage n
-            constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
+        if (rank == 0) {  // ===== MMA issuer (rank 0 of a pair): half n accumulates in TMEM stage n; whole warp, one elected lane issues
+            constexpr uint32_t idesc = ptx::make_idesc_f16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, it++) {
+            const uint32_t smem_base = ptx::smem_u32(smem);
+            for (int m_blk = blk_first; m_blk < num_m; m_blk += blk_step, it++) {
                 for (int as = 0; as < 2; as++) {
                     ptx::mbar_wait(&tmem_empty[as], (it & 1) ^ 1);
                     ptx::tc_fence_after();
@@ -622,16 +667,24 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     for (int kb = 0; kb < num_k; kb++) {
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after();
-                        const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+                        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(sa);
                         const uint64_t b_desc = ptx::make_sw128_kmajor_desc(sa + L::A_BYTES);
+                        if (ptx::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; k++)
-                            ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                        ptx::umma_commit(&empty_bar[stage]);
+                            for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                                if (PAIR) ptx::umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                                else ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                            }
+                            if (PAIR) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+                        }
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    ptx::umma_commit(&tmem_full[as]);
+                    if (ptx::elect_one()) {
+                        if (PAIR) ptx::umma_commit_pair(&tmem_full[as]); else ptx::umma_commit(&tmem_full[as]);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -646,7 +699,7 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         float2* stat = reinterpret_cast<float2*>(smem + L::STAT_OFFSET);
         uint32_t res_phase = 0;
         int it = 0;
-        for (int m_blk = blockIdx.x; m_blk < num_m; m_blk += gridDim.x, it++) {
+        for (int m_blk = blk_first; m_blk < num_m + rank; m_blk += blk_step, it++) {
             const int row0 = m_blk * BLOCK_M + quarter * 32;
             if (lane == 0) {
                 ptx::bulk_wait_read<0>();  // the previous row block's stores no longer read the boxes
@@ -703,7 +756,9 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty[n_blk]);  // accumulator stage free for the next row block
+                if (lane == 0) {  // accumulator stage free for the next row block
+                    if (PAIR) ptx::mbar_arrive_leader(&tmem_empty[n_blk]); else ptx::mbar_arrive(&tmem_empty[n_blk]);
+                }
             }
             res_phase ^= 1;
             // ---- the two warps of a row quarter hold the two halves of each row's statistics
@@ -752,11 +807,29 @@ gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+                   const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   int M, int K, int wait_ns) {
+    gemm_f16_ln_body<BLOCK_N, STAGES, false>(tmap_a, tmap_b, tmap_c, tmap_r, bias, gamma, beta, eps, M, K, wait_ns);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_ln_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+                        const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float eps, int M, int K, int wait_ns) {
+    gemm_f16_ln_body<BLOCK_N, STAGES, true>(tmap_a, tmap_b, tmap_c, tmap_r, bias, gamma, beta, eps, M, K, wait_ns);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -962,6 +1035,12 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
     return true;
 }
 
+// CTA-pair (cta_group::2) variant of the fused-LayerNorm projection: LB2_GEMM_LN_PAIR=1/0 (read per call: the tests flip it)
+static bool gemm_ln_pair_enabled() {
+    const char* e = getenv("LB2_GEMM_LN_PAIR");
+    return e ? atoi(e) != 0 : false;
+}
+
 // x_out[M, 384] = LayerNorm(A[M, K] . W[384, K]^T + bias + residual) * gamma + beta  (gemm_f16_ln_kernel)
 bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, const __half* W, const float* bias,
                      const __half* residual, const float* gamma, const float* beta, float eps, __half* C, int M, int N, int K,
@@ -971,26 +1050,57 @@ bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tm
         set_error("gemm_f16_res_ln: unsupported shape M=%d N=%d K=%d (N must be %d)", M, N, K, 2 * GEMM_BLOCK_N);
         return false;
     }
-    constexpr int LN_STAGES = 3;
-    using L = GemmLnSmem<GEMM_BLOCK_N, LN_STAGES>;
     CUtensorMap ta, tb_local, tc, tr;
     if (!make_tmap_f16_2d(&ta, A, (uint64_t)M, (uint64_t)K, BLOCK_M, BLOCK_K)) return false;
     if (!make_tmap_f16_2d(&tc, C, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
     if (!make_tmap_f16_2d(&tr, residual, (uint64_t)M, (uint64_t)N, 32, 32)) return false;
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool dev_ok = dev >= 0 && dev < 256;
+    if (gemm_ln_pair_enabled() && num_m >= 2) {
+        // CTA pairs (cta_group::2): each CTA loads half of the W rows of a panel -> its own tensor map (96-row boxes)
+        constexpr int PAIR_STAGES = 4;
+        using L = GemmLnSmem<GEMM_BLOCK_N, PAIR_STAGES, true>;
+        if (!make_tmap_f16_2d(&tb_local, W, (uint64_t)N, (uint64_t)K, GEMM_BLOCK_N / 2, BLOCK_K)) return false;
+        auto kern = gemm_f16_ln_pair_kernel<GEMM_BLOCK_N, PAIR_STAGES>;
+        static thread_local int attr_dev_mask[8] = {0};
+        static thread_local int max_clusters[256] = {0};
+        if (!dev_ok || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+            if (e != cudaSuccess) { set_error("gemm_f16_res_ln (pair): %s", cudaGetErrorString(e)); return false; }
+            if (dev_ok) {
+                attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(num_sms & ~1);
+                cfg.blockDim = dim3(GEMM_THREADS);
+                cfg.dynamicSmemBytes = L::TOTAL;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters[dev] = n;
+                else { cudaGetLastError(); max_clusters[dev] = num_sms / 2; }
+            }
+        }
+        int pairs = dev_ok ? max_clusters[dev] : num_sms / 2;  // co-resident pairs: the kernel is persistent
+        if (pairs > num_sms / 2) pairs = num_sms / 2;
+        if (pairs > (num_m + 1) / 2) pairs = (num_m + 1) / 2;
+        kern<<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb_local, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns());
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("gemm_f16_res_ln (pair) launch: %s", cudaGetErrorString(e)); return false; }
+        return true;
+    }
+    constexpr int LN_STAGES = 3;
+    using L = GemmLnSmem<GEMM_BLOCK_N, LN_STAGES, false>;
     if (!tmap_w) {
         if (!make_tmap_f16_2d(&tb_local, W, (uint64_t)N, (uint64_t)K, GEMM_BLOCK_N, BLOCK_K)) return false;
         tmap_w = &tb_local;
     }
     auto kern = gemm_f16_ln_kernel<GEMM_BLOCK_N, LN_STAGES>;
     static thread_local int attr_dev_mask[8] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 256 || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
+    if (!dev_ok || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
         if (e != cudaSuccess) { set_error("gemm_f16_res_ln: %s", cudaGetErrorString(e)); return false; }
-        if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
+        if (dev_ok) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
-    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
     const int grid = num_m < num_sms ? num_m : num_sms;
     kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns());
     cudaError_t e = cudaGetLastError();

@@ -123,3 +123,29 @@ def test_gemm_res_ln_fused_vs_torch(lib, cuda_ok, M, K):
     err = (C.float() - ref).abs()
     tol = 4e-3 + 2e-3 * ref.abs()  # fp16 output rounding + an fp16 ulp of the pre-norm value flipping under accumulation-order noise
     assert (err <= tol).all(), f"max err {err.max().item()} at {torch.nonzero(err > tol)[:3].tolist()}"
+
+
+@pytest.mark.parametrize("M", [1, 129, 256, 257, 1000, 148 * 128 + 77, 40000])
+@pytest.mark.parametrize("K", [384, 1536])
+def test_gemm_res_ln_cta_pair_matches_single_cta(lib, cuda_ok, M, K, monkeypatch):
+    """The cta_group::2 variant of the fused Linear + residual + LayerNorm (two CTAs share the W panel) against the
+    single-CTA kernel: same accumulation order per row, so the results are identical."""
+    N = 384
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    res = torch.randn(M, N, device="cuda", generator=g).half()
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    beta = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("LB2_GEMM_LN_PAIR", pair)
+        C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+        rc = lib.lb2_test_gemm_res_ln_f16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), res.data_ptr(), gamma.data_ptr(),
+                                          beta.data_ptr(), 1e-12, C.data_ptr(), M, N, K)
+        assert rc == 0, lib.lb2_last_error()
+        torch.cuda.synchronize()
+        out.append(C)
+    assert torch.isfinite(out[0]).all()
+    assert torch.equal(out[0], out[1])

@@ -44,8 +44,11 @@ def test_errors_and_edge_cases(lib, cuda_ok, golden, tmp_path):
     with pytest.raises(capi.Lb2Error, match="lb2_set_passages"):
         idx.search(golden["q"], 10, capi.make_params(recompute=True))
     idx.set_vectors(golden["x"])
-    with pytest.raises(capi.Lb2Error, match="not implemented"):
-        idx.search(golden["q"], 10, capi.make_params(prune_ratio=0.5, recompute=False))
+    # pruning parameters without loaded PQ tables are ignored, as in the reference (perform_pq_pruning needs an
+    # initialised pq_data_loader, HNSW_search.cpp:442-445)
+    D0, I0 = idx.search(golden["q"], 10, capi.make_params(recompute=False))
+    D1, I1 = idx.search(golden["q"], 10, capi.make_params(prune_ratio=0.5, recompute=False))
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
     D, I = idx.search(golden["q"][:0], 10, capi.make_params(recompute=False))
     assert D.shape == (0, 10)
     # k larger than what a tiny graph can return: unfilled slots are (-1, -FLT_MAX) like faiss
