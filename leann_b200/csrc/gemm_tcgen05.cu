@@ -1035,10 +1035,11 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
     return true;
 }
 
-// CTA-pair (cta_group::2) variant of the fused-LayerNorm projection: LB2_GEMM_LN_PAIR=1/0 (read per call: the tests flip it)
+// CTA-pair (cta_group::2) variant of the fused-LayerNorm projection, the default; LB2_GEMM_LN_PAIR=0 selects the single-CTA
+// kernel (read per call: the tests flip it)
 static bool gemm_ln_pair_enabled() {
     const char* e = getenv("LB2_GEMM_LN_PAIR");
-    return e ? atoi(e) != 0 : false;
+    return e ? atoi(e) != 0 : true;
 }
 
 // x_out[M, 384] = LayerNorm(A[M, K] . W[384, K]^T + bias + residual) * gamma + beta  (gemm_f16_ln_kernel)
