@@ -64,7 +64,7 @@ template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                   const float* __restrict__ bias, int M, int N, int K, int c_group, int wait_ns) {
+                   const float* __restrict__ bias, int M, int N, int K, int c_group, int wait_ns, int pf_tiles) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                             : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -121,10 +121,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             for (int kb = 0; kb < num_k; kb++) {
+                // the A k-block this CTA loads `pf_tiles` k-blocks from now: into L2 (of the num_n CTAs that read a row
+                // block at about the same time, the one working on column block 0 asks)
+                const int pf_it = (kb + pf_tiles) / num_k, pf_kb = (kb + pf_tiles) - pf_it * num_k;
+                const int pf_tile = tile + pf_it * gridDim.x;
+                const bool pf = pf_tiles > 0 && pf_tile < num_tiles && pf_tile % num_n == 0;
                 ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
                 uint8_t* sa = smem + stage * L::STAGE_BYTES;
                 uint8_t* sb = sa + L::A_BYTES;
                 if (ptx::elect_one()) {
+                    if (pf) ptx::tma_prefetch_2d(&tmap_a, pf_kb * BLOCK_K, (pf_tile / num_n) * BLOCK_M);
                     ptx::mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
                     ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
@@ -309,7 +315,7 @@ template <int BLOCK_N, int NUM_K, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, int M, int N, int c_group,
-                   int ctas_per_panel) {
+                   int ctas_per_panel, int pf_tiles) {
     using L = GemmWsSmem<BLOCK_N, NUM_K, STAGES>;
     static_assert(L::TOTAL <= 232448, "shared memory budget");
     static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU, "no residual variant");
@@ -392,8 +398,13 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 cur_n = n_blk;
             }
             for (int kb = 0; kb < NUM_K; kb++) {
+                // the A k-block this CTA loads `pf_tiles` k-blocks from now: into L2 (only the CTAs of panel 0 ask — the
+                // others read the same rows at the same time)
+                const int pf_it = (kb + pf_tiles) / NUM_K, pf_kb = (kb + pf_tiles) - pf_it * NUM_K;
+                const bool pf = pf_tiles > 0 && n_blk == 0 && tile + pf_it < t_end;
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (ptx::elect_one()) {
+                    if (pf) ptx::tma_prefetch_2d(&tmap_a, pf_kb * BLOCK_K, (m_blk + pf_it) * BLOCK_M);
                     ptx::mbar_expect_tx(&full_bar[stage], L::A_BYTES);
                     ptx::tma_load_2d(smem + L::A_OFFSET + stage * L::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K,
                                      m_blk * BLOCK_M);
@@ -568,7 +579,7 @@ template <int BLOCK_N, int STAGES, bool PAIR>
 __device__ __forceinline__ void
 gemm_f16_ln_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_c, const CUtensorMap& tmap_r,
                  const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                 int M, int K, int wait_ns) {
+                 int M, int K, int wait_ns, int pf_tiles) {
     using L = GemmLnSmem<BLOCK_N, STAGES, PAIR>;
     const int rank = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;
     // row blocks are dealt to CTAs (pairs: to the pair, rank r takes the r-th of two consecutive ones; a block past the end
@@ -631,10 +642,16 @@ gemm_f16_ln_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUt
         for (int m_blk = blk_first; m_blk < num_m + rank; m_blk += blk_step) {
             for (int n_blk = 0; n_blk < 2; n_blk++) {
                 for (int kb = 0; kb < num_k; kb++) {
+                    // the A k-block this CTA loads `pf_tiles` first-pass k-blocks from now: into L2 (the second column half
+                    // re-reads what the first one loaded)
+                    const int pf_it = (kb + pf_tiles) / num_k, pf_kb = (kb + pf_tiles) - pf_it * num_k;
+                    const int pf_blk = m_blk + pf_it * blk_step;
+                    const bool pf = pf_tiles > 0 && n_blk == 0 && pf_blk < num_m;
                     ptx::mbar_wait_ns(&empty_bar[stage], phase ^ 1, wait_ns * 8);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
                     if (ptx::elect_one()) {
+                        if (pf) ptx::tma_prefetch_2d(&tmap_a, pf_kb * BLOCK_K, pf_blk * BLOCK_M);
                         if (PAIR) {
                             // both CTAs' bytes complete on rank 0's barrier; rank 0 announces the total
                             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
@@ -819,8 +836,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   int M, int K, int wait_ns) {
-    gemm_f16_ln_body<BLOCK_N, STAGES, false>(tmap_a, tmap_b, tmap_c, tmap_r, bias, gamma, beta, eps, M, K, wait_ns);
+                   int M, int K, int wait_ns, int pf_tiles) {
+    gemm_f16_ln_body<BLOCK_N, STAGES, false>(tmap_a, tmap_b, tmap_c, tmap_r, bias, gamma, beta, eps, M, K, wait_ns, pf_tiles);
 }
 
 template <int BLOCK_N, int STAGES>
@@ -828,8 +845,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_ln_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
                         const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
-                        float eps, int M, int K, int wait_ns) {
-    gemm_f16_ln_body<BLOCK_N, STAGES, true>(tmap_a, tmap_b, tmap_c, tmap_r, bias, gamma, beta, eps, M, K, wait_ns);
+                        float eps, int M, int K, int wait_ns, int pf_tiles) {
+    gemm_f16_ln_body<BLOCK_N, STAGES, true>(tmap_a, tmap_b, tmap_c, tmap_r, bias, gamma, beta, eps, M, K, wait_ns, pf_tiles);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -929,6 +946,16 @@ static int gemm_wait_ns() {
 constexpr int GEMM_BLOCK_N = 192;
 constexpr int GEMM_STAGES = 4;
 
+// How many k-blocks ahead of its loads the producer asks L2 for the activation rows (cp.async.bulk.prefetch.tensor).  The
+// shared-memory ring only covers 4 k-blocks = ~1 500 tensor clocks of work, while a TMA load of rows that are not in L2 yet
+// takes ~3 000 clocks under load (ncu: the MMA warp spent 42 % of its samples on the `full` barriers); the prefetch turns
+// those loads into L2 hits without spending shared memory (12 k-blocks x 16 KB x 148 CTAs = 28 MB outstanding, L2 is 126 MB).
+// LB2_GEMM_PF overrides (0 = off).
+static int gemm_prefetch_tiles() {
+    static const int v = getenv("LB2_GEMM_PF") ? atoi(getenv("LB2_GEMM_PF")) : 12;
+    return v;
+}
+
 template <int EPI>
 static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                                const CUtensorMap& tr, const float* bias, int M, int N, int K, int c_group, int num_sms) {
@@ -944,7 +971,7 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group, gemm_wait_ns());
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group, gemm_wait_ns(), gemm_prefetch_tiles());
     return cudaGetLastError();
 }
 
@@ -979,7 +1006,7 @@ static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, co
         const long long tiles = static_cast<long long>(num_m) * num_n;
         grid = tiles < num_sms ? static_cast<int>(tiles) : num_sms;
     }
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N, c_group, cpp);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N, c_group, cpp, gemm_prefetch_tiles());
     return cudaGetLastError();
 }
 
@@ -1084,7 +1111,8 @@ bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tm
         int pairs = dev_ok ? max_clusters[dev] : num_sms / 2;  // co-resident pairs: the kernel is persistent
         if (pairs > num_sms / 2) pairs = num_sms / 2;
         if (pairs > (num_m + 1) / 2) pairs = (num_m + 1) / 2;
-        kern<<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb_local, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns());
+        kern<<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb_local, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns(),
+                                                             gemm_prefetch_tiles());
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("gemm_f16_res_ln (pair) launch: %s", cudaGetErrorString(e)); return false; }
         return true;
@@ -1103,7 +1131,7 @@ bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tm
         if (dev_ok) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
     const int grid = num_m < num_sms ? num_m : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns());
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns(), gemm_prefetch_tiles());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("gemm_f16_res_ln launch: %s", cudaGetErrorString(e)); return false; }
     return true;

@@ -81,6 +81,12 @@ __device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, uns
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// Ask L2 to fetch the box (no shared-memory destination, no completion): a later load of the same box hits L2.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
 // 2D tiled load, completes `bytes` on `bar`.  c0 = innermost (contiguous) coordinate.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile(
