@@ -950,9 +950,16 @@ constexpr int GEMM_STAGES = 4;
 // shared-memory ring only covers 4 k-blocks = ~1 500 tensor clocks of work, while a TMA load of rows that are not in L2 yet
 // takes ~3 000 clocks under load (ncu: the MMA warp spent 42 % of its samples on the `full` barriers); the prefetch turns
 // those loads into L2 hits without spending shared memory (12 k-blocks x 16 KB x 148 CTAs = 28 MB outstanding, L2 is 126 MB).
-// LB2_GEMM_PF overrides (0 = off).
+// Measured (profiles/r02c_gemm_prefetch_sweep.log): the weight-stationary kernel gains 3-4 % on the QKV shape with 6-12
+// k-blocks, nothing on FFN-up; the streaming kernels (which also stream W) LOSE 10-30 % at K = 1536 — their prefetches
+// compete with the loads they are meant to help — so only the weight-stationary kernel prefetches by default.
+// LB2_GEMM_PF / LB2_GEMM_PF_STREAM override (0 = off).
 static int gemm_prefetch_tiles() {
     static const int v = getenv("LB2_GEMM_PF") ? atoi(getenv("LB2_GEMM_PF")) : 12;
+    return v;
+}
+static int gemm_prefetch_tiles_stream() {
+    static const int v = getenv("LB2_GEMM_PF_STREAM") ? atoi(getenv("LB2_GEMM_PF_STREAM")) : 0;
     return v;
 }
 
@@ -971,7 +978,7 @@ static cudaError_t launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * (N / GEMM_BLOCK_N);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group, gemm_wait_ns(), gemm_prefetch_tiles());
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, tr, bias, M, N, K, c_group, gemm_wait_ns(), gemm_prefetch_tiles_stream());
     return cudaGetLastError();
 }
 
@@ -1112,7 +1119,7 @@ bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tm
         if (pairs > num_sms / 2) pairs = num_sms / 2;
         if (pairs > (num_m + 1) / 2) pairs = (num_m + 1) / 2;
         kern<<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb_local, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns(),
-                                                             gemm_prefetch_tiles());
+                                                             gemm_prefetch_tiles_stream());
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("gemm_f16_res_ln (pair) launch: %s", cudaGetErrorString(e)); return false; }
         return true;
@@ -1131,7 +1138,7 @@ bool gemm_f16_res_ln(cudaStream_t stream, const __half* A, const CUtensorMap* tm
         if (dev_ok) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
     const int grid = num_m < num_sms ? num_m : num_sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns(), gemm_prefetch_tiles());
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, *tmap_w, tc, tr, bias, gamma, beta, eps, M, K, gemm_wait_ns(), gemm_prefetch_tiles_stream());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("gemm_f16_res_ln launch: %s", cudaGetErrorString(e)); return false; }
     return true;
