@@ -20,19 +20,21 @@ __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ CUtensorMap m
         ptx::fence_barrier_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // whole warp, one elected issuer; cheap index arithmetic (the loop must not be the limiter)
         const long long t0 = clock64();
-        // keep `stages` loads in flight: wait for the oldest, re-issue into its slot
+        int s = 0, par = 0, blk = (blockIdx.x * 37) % row_blocks, kc = 0;
         for (int i = 0; i < iters + stages; i++) {
-            const int s = i % stages;
-            if (i >= stages) ptx::mbar_wait(&bars[s], ((i / stages) - 1) & 1);
-            if (i < iters) {
-                const int blk = (blockIdx.x * 7919 + i * 131) % row_blocks;   // scattered over the matrix
+            if (i >= stages) ptx::mbar_wait(&bars[s], par ^ 1);
+            if (i < iters && ptx::elect_one()) {
                 ptx::mbar_expect_tx(&bars[s], box_bytes);
-                ptx::tma_load_2d(smem + s * box_bytes, &map, &bars[s], (i % 6) * 64, blk * box_rows);
+                ptx::tma_load_2d(smem + s * box_bytes, &map, &bars[s], kc * 64, blk * box_rows);
             }
+            __syncwarp();
+            if (++kc == 6) { kc = 0; blk += 149; if (blk >= row_blocks) blk -= row_blocks; }
+            if (++s == stages) { s = 0; par ^= 1; }
         }
-        out[blockIdx.x] = clock64() - t0;
+        if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
     }
 }
 
