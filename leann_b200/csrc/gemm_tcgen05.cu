@@ -315,7 +315,7 @@ template <int BLOCK_N, int NUM_K, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, int M, int N, int c_group,
-                   int ctas_per_panel, int pf_tiles, int exp_flags) {
+                   int ctas_per_panel, int pf_tiles, int exp_flags, __half* __restrict__ C) {
     using L = GemmWsSmem<BLOCK_N, NUM_K, STAGES>;
     static_assert(L::TOTAL <= 232448, "shared memory budget");
     static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU, "no residual variant");
@@ -511,10 +511,30 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
                     for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
                 }
+                uint8_t* box = box_base + lane * 64;
+                if (exp_flags & 2) {
+                    // direct stores: the box only transposes (thread = row  ->  4 lanes = one 64-byte row segment), the
+                    // warp writes 8 rows x 64 B per instruction itself; no TMA store, no async-proxy fence, no wait for the
+                    // TMA unit to have read the box
+                    __syncwarp();  // the previous chunk's reads of the box are done
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) *reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4)) = ov[j4];
+                    __syncwarp();
+                    const int piece = lane & 3;
+                    __half* cbase = c_group > 0 ? C + (static_cast<size_t>(col0 / c_group) * M) * c_group + col0 % c_group
+                                                : C + col0;
+                    const size_t pitch = c_group > 0 ? c_group : N;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int r = 8 * i + (lane >> 2);
+                        const uint4 v = *reinterpret_cast<const uint4*>(box_base + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
+                        if (row0 + r < M) *reinterpret_cast<uint4*>(cbase + (row0 + r) * pitch + piece * 8) = v;
+                    }
+                    continue;
+                }
                 // the store issued from this warp's box one chunk ago must have finished reading it
                 if (lane == 0) ptx::bulk_wait_read<0>();
                 __syncwarp();
-                uint8_t* box = box_base + lane * 64;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) *reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4)) = ov[j4];
                 ptx::fence_async_smem();
@@ -992,7 +1012,7 @@ static bool gemm_ws_enabled() {
 
 template <int EPI>
 static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                                  const float* bias, int M, int N, int c_group, int num_sms) {
+                                  const float* bias, int M, int N, int c_group, int num_sms, __half* C) {
     using L = GemmWsSmem<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES>;
     auto kern = gemm_f16_ws_kernel<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES, EPI>;
     static thread_local int attr_dev_mask[8] = {0};
@@ -1014,7 +1034,7 @@ static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, co
         grid = tiles < num_sms ? static_cast<int>(tiles) : num_sms;
     }
     kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N, c_group, cpp, gemm_prefetch_tiles(),
-                                                    getenv("LB2_GEMM_EXP") ? atoi(getenv("LB2_GEMM_EXP")) : 0);
+                                                    getenv("LB2_GEMM_EXP") ? atoi(getenv("LB2_GEMM_EXP")) : 0, C);
     return cudaGetLastError();
 }
 
@@ -1049,8 +1069,8 @@ bool gemm_f16(cudaStream_t stream, const __half* A, const CUtensorMap* tmap_w, c
     }
     cudaError_t e;
     if (K == WS_NUM_K * BLOCK_K && epi != EPI_BIAS_RES && gemm_ws_enabled()) {
-        e = epi == EPI_BIAS ? launch_gemm_ws<EPI_BIAS>(stream, ta, *tmap_w, tc, bias, M, N, c_group, num_sms)
-                            : launch_gemm_ws<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, bias, M, N, c_group, num_sms);
+        e = epi == EPI_BIAS ? launch_gemm_ws<EPI_BIAS>(stream, ta, *tmap_w, tc, bias, M, N, c_group, num_sms, C)
+                            : launch_gemm_ws<EPI_BIAS_GELU>(stream, ta, *tmap_w, tc, bias, M, N, c_group, num_sms, C);
         if (e != cudaSuccess) {
             set_error("gemm_f16 (weight-stationary) launch: %s", cudaGetErrorString(e));
             return false;
