@@ -1010,11 +1010,11 @@ static bool gemm_ws_enabled() {
     return v;
 }
 
-template <int EPI>
-static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+template <int EPI, int WS_STAGES_T>
+static cudaError_t launch_gemm_ws_s(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                                   const float* bias, int M, int N, int c_group, int num_sms, __half* C) {
-    using L = GemmWsSmem<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES>;
-    auto kern = gemm_f16_ws_kernel<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES, EPI>;
+    using L = GemmWsSmem<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES_T>;
+    auto kern = gemm_f16_ws_kernel<GEMM_BLOCK_N, WS_NUM_K, WS_STAGES_T, EPI>;
     static thread_local int attr_dev_mask[8] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1036,6 +1036,16 @@ static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, co
     kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N, c_group, cpp, gemm_prefetch_tiles(),
                                                     getenv("LB2_GEMM_EXP") ? atoi(getenv("LB2_GEMM_EXP")) : 0, C);
     return cudaGetLastError();
+}
+
+// LB2_GEMM_WS_STAGES = 2 / 3 selects a shallower activation ring (depth-sensitivity experiment); default 4
+template <int EPI>
+static cudaError_t launch_gemm_ws(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                                  const float* bias, int M, int N, int c_group, int num_sms, __half* C) {
+    static const int st = getenv("LB2_GEMM_WS_STAGES") ? atoi(getenv("LB2_GEMM_WS_STAGES")) : WS_STAGES;
+    if (st == 2) return launch_gemm_ws_s<EPI, 2>(stream, ta, tb, tc, bias, M, N, c_group, num_sms, C);
+    if (st == 3) return launch_gemm_ws_s<EPI, 3>(stream, ta, tb, tc, bias, M, N, c_group, num_sms, C);
+    return launch_gemm_ws_s<EPI, WS_STAGES>(stream, ta, tb, tc, bias, M, N, c_group, num_sms, C);
 }
 
 // A [M,K] fp16 row-major, W [N,K] fp16 row-major (nn.Linear layout), C [M,N] fp16.
