@@ -51,9 +51,30 @@ __device__ void body(int N, int iters, int bg, long long* out) {
         ptx::mbar_wait(bar, 0);
         t1 = clock64();
         if ((threadIdx.x & 31) == 0) { out[blockIdx.x] = t1 - t0; *done = 1; }
-    } else if (warp >= 2 && bg) {
+    } else if (warp >= 4 && bg >= 3) {
+        // background tensor-memory reads (what a GEMM epilogue does while the next tile's MMAs run): 4 or 8 warps, each
+        // reading 32 lanes x 32 columns of fp32 per tcgen05.ld from the accumulator buffer the MMAs are NOT writing... both
+        // buffers alternate, so in effect from both
+        if (bg == 3 && warp >= 8) {}
+        else {
+            const uint32_t taddr = tm + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+            uint32_t r[32];
+            long long n = 0;
+            uint32_t acc = 0;
+            while (!*done) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    ptx::tmem_ld_32x32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    acc += r[0] ^ r[31];
+                }
+                n += 8;
+            }
+            if ((threadIdx.x & 31) == 0 && warp == 4) out[512 + blockIdx.x] = n + (acc == 12345);
+        }
+    } else if (warp >= 2 && warp < 4 && bg && bg < 3) {
         // background shared-memory traffic (what TMA fills and the epilogue's staging do in the GEMM): 16 B per lane per access
-        const uint32_t base = ptx::smem_u32(bgbuf) + (threadIdx.x - 64) * 16;
+        const uint32_t base = ptx::smem_u32(bgbuf) + (threadIdx.x - 64) * 16;  // warps 2 and 3
         uint32_t x0 = 1, x1 = 2, x2 = 3, x3 = 4;
         long long n = 0;
         while (!*done) {
@@ -74,8 +95,8 @@ __device__ void body(int N, int iters, int bg, long long* out) {
         if (PAIR) ptx::tmem_dealloc_pair(tm, 512); else ptx::tmem_dealloc(tm, 512);
     }
 }
-__global__ void __launch_bounds__(128, 1) k1(int N, int iters, int bg, long long* out) { body<false>(N, iters, bg, out); }
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(int N, int iters, int bg, long long* out) { body<true>(N, iters, bg, out); }
+__global__ void __launch_bounds__(384, 1) k1(int N, int iters, int bg, long long* out) { body<false>(N, iters, bg, out); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k2(int N, int iters, int bg, long long* out) { body<true>(N, iters, bg, out); }
 
 int main() {
     int sms = 0;
@@ -84,7 +105,7 @@ int main() {
     cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     const int iters = 20000;
-    for (int bg = 0; bg < 3; bg++)
+    for (int bg = 0; bg < 5; bg++)
     for (int pair = 0; pair < 2; pair++)
         for (int N : {64, 128, 192, 256}) {
             if (bg && N != 192 && N != 256) continue;
@@ -92,7 +113,7 @@ int main() {
             float ms = 0; cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             for (int rep = 0; rep < 2; rep++) {
                 cudaEventRecord(e0);
-                if (pair) k2<<<grid, 128, SMEM>>>(N, iters, bg, d); else k1<<<grid, 128, SMEM>>>(N, iters, bg, d);
+                if (pair) k2<<<grid, 384, SMEM>>>(N, iters, bg, d); else k1<<<grid, 384, SMEM>>>(N, iters, bg, d);
                 cudaEventRecord(e1);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
@@ -104,9 +125,10 @@ int main() {
             cyc /= n;
             const double mmas = 4.0 * iters;
             const double flops = 2.0 * (pair ? 256.0 : 128.0) * N * 16 * mmas * (pair ? grid / 2 : grid);
-            const double bgb = bg ? (double)h[512] * 64 * 16 / cyc : 0.0;  // 2 warps x 32 lanes x 16 B per access
+            // smem modes: 2 warps x 32 lanes x 16 B per access; TMEM modes: 4 / 8 warps x 4 KB per tcgen05.ld
+            const double bgb = bg == 0 ? 0.0 : bg < 3 ? (double)h[512] * 64 * 16 / cyc : (double)h[512] * (bg == 3 ? 4 : 8) * 4096 / cyc;
             printf("cta_group::%d M=%d N=%3d bg=%s: %7.1f clk per MMA (%.0f MAC/clk/SM), %.3f ms -> %.0f TFLOP/s, %.2f GHz, background %.0f B/clk/SM\n",
-                   pair + 1, pair ? 256 : 128, N, bg == 0 ? "none" : bg == 1 ? "ld.shared" : "st.shared", cyc / mmas,
+                   pair + 1, pair ? 256 : 128, N, bg == 0 ? "none" : bg == 1 ? "ld.shared" : bg == 2 ? "st.shared" : bg == 3 ? "tcgen05.ld x4 warps" : "tcgen05.ld x8 warps", cyc / mmas,
                    128.0 * N * 16 / (cyc / mmas), ms, flops / ms / 1e9, cyc / ms / 1e6, bgb);
         }
     return 0;
