@@ -34,13 +34,15 @@ constexpr int ATC_HD = 32;
 constexpr int ATC_TM = 128;    // query rows per item
 constexpr int ATC_MAXL = 256;  // keys per passage (TMEM columns of S)
 constexpr int ATC_BOX = 64;    // rows per TMA box
-constexpr int ATC_THREADS = 192;
+constexpr int ATC_THREADS = 192;     // 4 softmax warps + TMA + MMA
+constexpr int ATC_THREADS8 = 320;    // 8 softmax warps (two per row quarter, each half of the key chunks) + TMA + MMA
 constexpr int ATC_QK_BYTES = ATC_MAXL * 128;
 constexpr int ATC_V_BYTES = ATC_MAXL * 64;
 constexpr int ATC_STAGE_BYTES = ATC_QK_BYTES + ATC_V_BYTES;
 constexpr int ATC_STAGES = 2;
 constexpr int ATC_BAR_OFFSET = ATC_STAGES * ATC_STAGE_BYTES;
-constexpr int ATC_SMEM = ATC_BAR_OFFSET + 16 * 8 + 16 + 1024;
+constexpr int ATC_X_OFFSET = ATC_BAR_OFFSET + 256;          // 8-warp softmax: row maxima / partial sums exchanged between the two warps of a row
+constexpr int ATC_SMEM = ATC_X_OFFSET + 2 * 2 * 2 * 128 * 4 + 1024;
 constexpr int ATC_TMEM_COLS = 256;
 constexpr int ATC_O_COL0 = 192;  // two O accumulators of 32 columns at the top of the allocation
 constexpr int ATC_LONG = 192;    // an item whose S needs more columns than this overlaps them ("long" item)
@@ -73,7 +75,8 @@ __global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_start,
 //   softmax warps: for i: wait S(i) -> softmax -> P(i) | read O(i - 1) out while P.V(i) and S(i + 1) execute
 // so the chain per item is softmax -> P.V + S, and the O read-out, the TMA loads and the other CTA's softmax fill the gaps.
 // A long item (S wider than 192 columns) would overwrite the O accumulators: both sides drain the pending read-outs first.
-__global__ void __launch_bounds__(ATC_THREADS, 2)
+template <int SW>
+__global__ void __launch_bounds__(SW * 32 + 64, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
                     const int4* __restrict__ desc, const int* __restrict__ n_items, int heads, int hidden,
                     __half* __restrict__ ctx, unsigned wait_ns, int skip_empty) {
@@ -91,7 +94,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     const int total = *n_items * heads;
     const int n_it = total > static_cast<int>(blockIdx.x) ? (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 
-    if (warp == 4 && lane == 0) {
+    if (warp == SW && lane == 0) {
         ptx::prefetch_tmap(&tmap_qk);
         ptx::prefetch_tmap(&tmap_v);
         for (int i = 0; i < ATC_STAGES; i++) {
@@ -99,14 +102,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             ptx::mbar_init(&empty_bar[i], 1);
         }
         ptx::mbar_init(s_ready, 1);
-        ptx::mbar_init(p_ready, 4);
+        ptx::mbar_init(p_ready, SW);
         for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&o_ready[i], 1);
-            ptx::mbar_init(&o_free[i], 4);
+            ptx::mbar_init(&o_free[i], SW);
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == SW + 1) {
         ptx::tmem_alloc(tmem_ptr, ATC_TMEM_COLS);
         ptx::tmem_relinquish();
     }
@@ -115,7 +118,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 4) {
+    if (warp == SW) {
         // ===== TMA producer, whole warp + one elected issuer (the descriptor of the next item is fetched while this one's
         // loads are issued)
         int4 cur = n_it > 0 ? __ldg(&desc[blockIdx.x / heads]) : make_int4(0, 0, 0, 0);
@@ -141,7 +144,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             __syncwarp();
             cur = nxt;
         }
-    } else if (warp == 5) {
+    } else if (warp == SW + 1) {
         if (n_it > 0) {
             // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (warp-uniform control flow keeps the
             // descriptors in uniform registers; under `if (lane == 0)` every tcgen05.mma sat in an ELECT / R2UR.BROADCAST
@@ -195,7 +198,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
                 nxt = nn;
             }
         }
-    } else {
+    } else if (SW == 4) {
         // ===== softmax + output: thread = query row
         const float scale_log2 = rsqrtf(static_cast<float>(ATC_HD)) * 1.4426950408889634f;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
@@ -317,9 +320,137 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
         while (pend < n_it) readout(pend++);
     }
 
+    else {
+        // ===== softmax + output with EIGHT warps: warps w and w + 4 share the query rows of TMEM lane quarter w & 3 and split
+        // the 32-key chunks (even / odd).  Twice the warps per SM sub-partition for the exponentials and the tcgen05.ld
+        // latencies (the 4-warp version kept MUFU 33 % busy), half the softmax latency per item.  Costs: the row maximum and
+        // the row sum are combined through shared memory (one 64-thread named barrier per pair), and because P(c) is
+        // written over the columns of S chunk c / 2 — possibly the OTHER warp's — pass 2 runs in rounds of two chunks with a
+        // pair barrier between the reads and the writes of a round.
+        const float scale_log2 = rsqrtf(static_cast<float>(ATC_HD)) * 1.4426950408889634f;
+        const int q4 = warp & 3, hh = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+        float* xmax = reinterpret_cast<float*>(smem + ATC_X_OFFSET);  // [item parity][half][row]
+        float* xsum = xmax + 2 * 2 * 128;                              // [item parity][half][row]
+        auto pair_sync = [&]() {  // named barrier 1 + q4 of the two warps that share this row quarter (immediate ids: 5 barriers per CTA)
+            if (q4 == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q4 == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q4 == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+        };
+        long long out_off[2] = {-1, -1};
+        int pend = 0;
+
+        auto readout = [&](int j) {
+            const int b = j & 1;
+            uint32_t o[16];
+            ptx::mbar_wait(&o_ready[b], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x16(taddr + ATC_O_COL0 + 32 * b + 16 * hh, o);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&o_free[b]);
+            const long long off = b ? out_off[1] : out_off[0];
+            if (off >= 0) {
+                const float inv = 1.0f / (xsum[(b * 2 + 0) * 128 + row] + xsum[(b * 2 + 1) * 128 + row]);
+                uint4* dst = reinterpret_cast<uint4*>(ctx + off + 16 * hh);
+#pragma unroll
+                for (int v4 = 0; v4 < 2; v4++) {
+                    uint4 ov;
+                    ov.x = pack2(__uint_as_float(o[8 * v4 + 0]) * inv, __uint_as_float(o[8 * v4 + 1]) * inv);
+                    ov.y = pack2(__uint_as_float(o[8 * v4 + 2]) * inv, __uint_as_float(o[8 * v4 + 3]) * inv);
+                    ov.z = pack2(__uint_as_float(o[8 * v4 + 4]) * inv, __uint_as_float(o[8 * v4 + 5]) * inv);
+                    ov.w = pack2(__uint_as_float(o[8 * v4 + 6]) * inv, __uint_as_float(o[8 * v4 + 7]) * inv);
+                    dst[v4] = ov;
+                }
+            }
+        };
+
+        int4 cur = n_it > 0 ? __ldg(&desc[blockIdx.x / heads]) : make_int4(0, 0, 0, 0);
+        for (int it = 0; it < n_it; it++) {
+            const int w = blockIdx.x + it * gridDim.x;
+            const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;
+            const int h = w % heads;
+            const int qb = cur.z;
+            const int L = cur.y;
+            const int q = qb * ATC_TM + row;
+            const int nch = (skip_empty && qb * ATC_TM + q4 * 32 >= L) ? 0 : (L + 31) >> 5;
+            const int xb = (it & 1) * 2;
+            if (((L + 15) & ~15) > ATC_LONG) {  // the MMA warp waits for these before it may issue S(it)
+                pair_sync();                   // the partner's partial sums of item it - 1 are in shared memory
+                while (pend < it) readout(pend++);
+            }
+            ptx::mbar_wait(s_ready, it & 1);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            // pass 1: maximum over this warp's chunks, then over both warps of the row
+            float m = -INFINITY;
+            for (int c = hh; c < nch; c += 2) {
+                ptx::tmem_ld_32x32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+                if (c * 32 + 32 <= L) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) m = (c * 32 + j < L) ? fmaxf(m, __uint_as_float(r[j])) : m;
+                }
+            }
+            xmax[(xb + hh) * 128 + row] = m;
+            pair_sync();  // also orders the partner's partial sums of item it - 1 before the read-out below
+            m = fmaxf(m, xmax[(xb + (hh ^ 1)) * 128 + row]);
+            // pass 2 in rounds of two chunks (one per warp)
+            const float ms = m * scale_log2;
+            float sum = 0.f;
+            for (int c0 = 0; c0 < nch; c0 += 2) {
+                const int c = c0 + hh;
+                const bool have = c < nch;
+                uint32_t pk[16];
+                if (have) {
+                    ptx::tmem_ld_32x32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    if (c * 32 + 32 <= L) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float p0 = ex2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms));
+                            const float p1 = ex2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms));
+                            sum += p0 + p1;
+                            pk[j] = pack2(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            float p0 = ex2f(fmaf(__uint_as_float(r[2 * j]), scale_log2, -ms));
+                            float p1 = ex2f(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -ms));
+                            p0 = (c * 32 + 2 * j < L) ? p0 : 0.f;
+                            p1 = (c * 32 + 2 * j + 1 < L) ? p1 : 0.f;
+                            sum += p0 + p1;
+                            pk[j] = pack2(p0, p1);
+                        }
+                    }
+                }
+                pair_sync();  // both warps have read their chunk of this round: P may now cover the columns of S chunk c0 / 2
+                if (have) ptx::tmem_st_32x16(taddr + c * 16, pk);
+            }
+            xsum[(xb + hh) * 128 + row] = sum;
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_ready);
+            const long long off = q < L ? static_cast<long long>(cur.x + q) * hidden + h * ATC_HD : -1;
+            if (it & 1) out_off[1] = off; else out_off[0] = off;
+            while (pend < it) readout(pend++);
+            cur = nxt;
+        }
+        pair_sync();  // the partner's partial sums of the last item
+        while (pend < n_it) readout(pend++);
+    }
+
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == SW + 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, ATC_TMEM_COLS);
     }
@@ -348,7 +479,8 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 256 || !(attr_dev_mask[dev >> 5] & (1 << (dev & 31)))) {
-        LB2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        LB2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        LB2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
         if (dev >= 0 && dev < 256) attr_dev_mask[dev >> 5] |= 1 << (dev & 31);
     }
     // LB2_ATTN_WAIT_NS > 0: the TMA and MMA warps sleep that long between mbarrier polls instead of spinning (A/B switch)
@@ -360,8 +492,14 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
         const char* e = getenv("LB2_ATTN_SKIP");
         return e ? atoi(e) : 1;
     }();
-    attention_tc_kernel<<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx, wait_ns,
-                                                                  skip_empty);
+    // LB2_ATTN_WARPS = 4 / 8 softmax warps per CTA (read per call: the tests compare the two)
+    const char* sw = getenv("LB2_ATTN_WARPS");
+    if (sw && atoi(sw) == 4)
+        attention_tc_kernel<4><<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx, wait_ns,
+                                                                         skip_empty);
+    else
+        attention_tc_kernel<8><<<2 * num_sms, ATC_THREADS8, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx,
+                                                                          wait_ns, skip_empty);
     LB2_CUDA_OK(cudaGetLastError());
     return true;
 }
