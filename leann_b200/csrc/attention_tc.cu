@@ -492,9 +492,11 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
         const char* e = getenv("LB2_ATTN_SKIP");
         return e ? atoi(e) : 1;
     }();
-    // LB2_ATTN_WARPS = 4 / 8 softmax warps per CTA (read per call: the tests compare the two)
+    // LB2_ATTN_WARPS = 4 (default) / 8 softmax warps per CTA (read per call: the tests compare the two).  Measured
+    // (profiles/r02c_attention_variants.log): 8 warps are 3-8 % SLOWER — the item time is set by the MUFU work of the two
+    // co-resident CTAs plus the softmax -> P.V -> S chain, not by latency hiding inside the softmax.
     const char* sw = getenv("LB2_ATTN_WARPS");
-    if (sw && atoi(sw) == 4)
+    if (!sw || atoi(sw) != 8)
         attention_tc_kernel<4><<<2 * num_sms, ATC_THREADS, ATC_SMEM, s>>>(tm_qk, tm_v, desc, item_count, heads, hidden, ctx, wait_ns,
                                                                          skip_empty);
     else

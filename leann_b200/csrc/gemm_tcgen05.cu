@@ -315,7 +315,7 @@ template <int BLOCK_N, int NUM_K, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, int M, int N, int c_group,
-                   int ctas_per_panel, int pf_tiles, int exp_flags, __half* __restrict__ C) {
+                   int ctas_per_panel, int pf_tiles, int direct_store, __half* __restrict__ C) {
     using L = GemmWsSmem<BLOCK_N, NUM_K, STAGES>;
     static_assert(L::TOTAL <= 232448, "shared memory budget");
     static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU, "no residual variant");
@@ -512,8 +512,8 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     for (int u = 0; u < 4; u++) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
                 }
                 uint8_t* box = box_base + lane * 64;
-                if (exp_flags & 2) {
-                    // direct stores: the box only transposes (thread = row  ->  4 lanes = one 64-byte row segment), the
+                if (direct_store) {
+                    // direct stores (LB2_GEMM_WS_DIRECT_STORE=1; measured 5-9 % slower than the TMA stores, kept as a tested alternative): the box only transposes (thread = row  ->  4 lanes = one 64-byte row segment), the
                     // warp writes 8 rows x 64 B per instruction itself; no TMA store, no async-proxy fence, no wait for the
                     // TMA unit to have read the box
                     __syncwarp();  // the previous chunk's reads of the box are done
@@ -539,7 +539,7 @@ gemm_f16_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 for (int j4 = 0; j4 < 4; j4++) *reinterpret_cast<uint4*>(box + ((j4 ^ swz) << 4)) = ov[j4];
                 ptx::fence_async_smem();
                 __syncwarp();
-                if (lane == 0 && !(exp_flags & 1)) {  // exp_flags: timing experiments only (LB2_GEMM_EXP), results are wrong
+                if (lane == 0) {
                     if (c_group > 0)
                         ptx::tma_store_3d(&tmap_c, box_base, col0 % c_group, row0, col0 / c_group);
                     else
@@ -1034,7 +1034,7 @@ static cudaError_t launch_gemm_ws_s(cudaStream_t stream, const CUtensorMap& ta, 
         grid = tiles < num_sms ? static_cast<int>(tiles) : num_sms;
     }
     kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, bias, M, N, c_group, cpp, gemm_prefetch_tiles(),
-                                                    getenv("LB2_GEMM_EXP") ? atoi(getenv("LB2_GEMM_EXP")) : 0, C);
+                                                    getenv("LB2_GEMM_WS_DIRECT_STORE") ? atoi(getenv("LB2_GEMM_WS_DIRECT_STORE")) : 0, C);
     return cudaGetLastError();
 }
 

@@ -149,3 +149,42 @@ def test_gemm_res_ln_cta_pair_matches_single_cta(lib, cuda_ok, M, K, monkeypatch
         out.append(C)
     assert torch.isfinite(out[0]).all()
     assert torch.equal(out[0], out[1])
+
+
+def test_attention_tc_8_softmax_warps_matches_4(lib, cuda_ok, monkeypatch):
+    """The 8-softmax-warp variant of the tcgen05 attention kernel (pair barriers, chunk rounds) against the default: same
+    exponentials per element, the row sum is added in a different order -> equal within an fp16 ulp of the output."""
+    H, heads = 384, 12
+    lens = [1, 2, 15, 17, 31, 33, 63, 65, 100, 128, 129, 160, 192, 193, 200, 255, 256] * 3
+    T = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(heads, T, 96, device="cuda", generator=g) * 1.5).half()
+    dl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    ds = (torch.cumsum(dl, 0) - dl).to(torch.int32)
+    out = []
+    for sw in ("8", "4"):
+        monkeypatch.setenv("LB2_ATTN_WARPS", sw)
+        ctx = torch.full((T, H), float("nan"), device="cuda", dtype=torch.float16)
+        assert lib.lb2_test_attention_f16(qkv.data_ptr(), ds.data_ptr(), dl.data_ptr(), len(lens), T, H, heads, 256, ctx.data_ptr()) == 0, lib.lb2_last_error()
+        torch.cuda.synchronize()
+        out.append(ctx.float())
+    assert torch.isfinite(out[0]).all()
+    assert (out[0] - out[1]).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("M", [129, 5000])
+@pytest.mark.parametrize("epi", [0, 1])
+def test_gemm_weight_stationary_direct_store_matches_tma_store(lib, cuda_ok, M, epi, monkeypatch):
+    N, K = 1536, 384
+    g = torch.Generator(device="cuda").manual_seed(M)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = []
+    for v in ("1", "0"):
+        monkeypatch.setenv("LB2_GEMM_WS_DIRECT_STORE", v)
+        C = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+        assert lib.lb2_test_gemm_f16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), 0, C.data_ptr(), M, N, K, epi) == 0, lib.lb2_last_error()
+        torch.cuda.synchronize()
+        out.append(C)
+    assert torch.isfinite(out[0]).all() and torch.equal(out[0], out[1])
