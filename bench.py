@@ -377,15 +377,19 @@ def run_b200(args):
         peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained, cuBLAS bf16 sustained)" if peaks else "fallback 1590"
         gemm_tf = agg["gemm_flops"] / (agg["gemm_ms"] / 1e3) / 1e12 if agg["gemm_ms"] > 0 else None
-        traffic = None
+        traffic, tr_ratio, tr_name = None, float("nan"), "none"
         try:  # DRAM bytes per GEMM launch = algorithmic bytes x the dram/algorithmic ratio of the committed ncu --set full capture
-            tr = json.loads((ROOT / "profiles" / "r01_final_gemm_traffic.json").read_text())
+            tr_file = ROOT / "profiles" / "r02_gemm_traffic.json"
+            if not tr_file.exists():
+                tr_file = ROOT / "profiles" / "r01_final_gemm_traffic.json"
+            tr = json.loads(tr_file.read_text())
             p_ = W["preset"]
             h, f = p_.hidden, p_.ffn
             bytes_tok_layer = 2 * ((h + 3 * h) + (3 * h) + (h + f) + (f + 2 * h))
             n_gemm = agg["passes"] * 4 * p_.layers
             if n_gemm > 0:
                 traffic = agg["n_tokens"] * p_.layers * bytes_tok_layer * tr["dram_over_algorithmic"] / n_gemm
+            tr_ratio, tr_name = tr["dram_over_algorithmic"], "profiles/" + tr_file.name
         except Exception:
             pass
         nqs = nq * args.steps  # this rank's queries (stats are per rank)
@@ -405,9 +409,10 @@ def run_b200(args):
                     "wall_s_timed_region": t_wall},
             "gpu_launches": int(agg["launches"]),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05)", "achieved": gemm_tf, "peak": peak,
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMMs of the encoder: gemm_f16_ws_kernel (QKV, FFN-up) + gemm_f16_ln_pair_kernel (out-proj / FFN-down fused with residual + LayerNorm)",
+                         "achieved": gemm_tf, "peak": peak,
                          "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None, "traffic": traffic,
-                         "traffic_note": "bytes per launch (average launch of the timed region); dram bytes = 1.01 x algorithmic in the ncu capture",
+                         "traffic_note": f"bytes per launch (average launch of the timed region); dram bytes = {tr_ratio:.2f} x algorithmic in the ncu capture ({tr_name})",
                          "peak_source": peak_src,
                          "share_of_step": agg["gemm_ms"] / agg["gpu_ms"] if agg["gpu_ms"] else None},
             "detail": {"ndis_per_query": agg["ndis"] / nqs, "nhops_per_query": agg["nhops"] / nqs,
