@@ -12,7 +12,7 @@ out.mkdir(exist_ok=True)
 
 
 def short(name):
-    m = re.search(r"(gemm_f16_(?:tn|ws)_kernel<[^>]*>|[a-z_]+_kernel(?:<[^>]*>)?)", name)
+    m = re.search(r"(gemm_f16_(?:tn|ws)_kernel<[^>]*>|[a-z0-9_]+_kernel(?:<[^>]*>)?)", name)
     return m.group(1) if m else name[:60]
 
 
