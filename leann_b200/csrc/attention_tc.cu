@@ -57,16 +57,32 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// work list: one descriptor per (passage, 128-row query block): {first packed row of the passage, length, query block, passage}.
+// work list: one descriptor per (passage, 128-row query block): {first packed row of the passage, length, query window, passage}.
 // One 16-byte load per work item in the kernel (no dependent items -> seq_len -> seq_start chain); a passage's blocks are adjacent.
+// query window z = q0 | lo << 16: the item's 128 MMA rows are the passage's rows [q0, q0 + 128); rows in [lo, L) are its
+// output.  First block: q0 = lo = 0.  Second block (rows 128 .. L-1, usually only one or two warps' worth): its rows may sit
+// in ANY row quarter of the tile — q0 = 128 - 32 * rot puts them rot quarters up (the A operand is the same (q | k) tile,
+// only the descriptor start moves by rot * 4 KB; the rows below lo are first-block rows whose warps idle).  Softmax warp w
+// lives on SM sub-partition w, and the exponentials of a sub-partition are the bound of this kernel: with every tail in
+// quarter 0, sub-partition 0 carried 1.31x the mean MUFU load on the bench corpus' length mix (N(128, 48)) and sub-partition
+// 3 0.72x.  The rotation is drawn per passage from small tables weighted towards the upper quarters (short first blocks load
+// the lower ones): max / mean = 1.01 on that mix (scripts in DESIGN.md §3).
+__constant__ uint8_t ATC_ROT1[8] = {3, 3, 3, 3, 3, 3, 0, 1};  // tail of <= 32 rows
+__constant__ uint8_t ATC_ROT2[8] = {2, 2, 2, 2, 2, 0, 0, 0};  // tail of <= 64 rows (<= 96 and more: no rotation)
 __global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len, int n_seq,
-                                          int row_base, int4* __restrict__ desc, int* __restrict__ count) {
+                                          int row_base, int4* __restrict__ desc, int* __restrict__ count, int rotate) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seq) return;
     const int L = seq_len[s];
     const int nb = (L + ATC_TM - 1) / ATC_TM;
     const int base = atomicAdd(count, nb);
-    for (int i = 0; i < nb; i++) desc[base + i] = make_int4(seq_start[s] - row_base, L, i, s);
+    desc[base] = make_int4(seq_start[s] - row_base, L, 0, s);
+    if (nb > 1) {
+        const int wt = (L - ATC_TM + 31) >> 5;  // warps the tail occupies
+        const unsigned hsh = (static_cast<unsigned>(s) * 2654435761u) >> 13;
+        const int rot = !rotate ? 0 : wt == 1 ? ATC_ROT1[hsh & 7] : wt == 2 ? ATC_ROT2[hsh & 7] : 0;
+        desc[base + 1] = make_int4(seq_start[s] - row_base, L, (ATC_TM - 32 * rot) | (ATC_TM << 16), s);
+    }
 }
 
 // Pipeline of one CTA over its items i = 0, 1, ... (two CTAs per SM interleave):
@@ -152,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             auto issue_s = [&](int it, const int4& d) {
                 const int Lp = (d.y + 15) & ~15;
                 const uint32_t qk = ptx::smem_u32(smem + (it & 1) * ATC_STAGE_BYTES);
-                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + d.z * ATC_TM * 128);
+                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(qk + (d.z & 0xffff) * 128);  // query window start q0 (a multiple of 32 rows = 4 KB)
                 const uint64_t b_desc = ptx::make_sw128_kmajor_desc(qk) + 4;  // the k half of the (q | k) rows: +64 B
                 const uint32_t idesc_s = ptx::make_idesc_f16(ATC_TM, Lp);
                 if (ptx::elect_one()) {
@@ -237,12 +253,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             const int w = blockIdx.x + it * gridDim.x;
             const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;  // in flight during this item's softmax
             const int h = w % heads;
-            const int qb = cur.z;
+            const int q0 = cur.z & 0xffff, lo = cur.z >> 16;
             const int L = cur.y;
-            const int q = qb * ATC_TM + threadIdx.x;
-            // a warp whose 32 query rows all lie beyond the passage (short passages, second query block) runs zero key
-            // chunks: no exponentials, no P rows (its O rows are never stored) — only the barrier protocol
-            const int nch = (skip_empty && qb * ATC_TM + warp * 32 >= L) ? 0 : (L + 31) >> 5;
+            const int q = q0 + threadIdx.x;
+            // a warp whose 32 query rows all lie outside [lo, L) (short passages; second query block: rows beyond the passage
+            // and first-block rows under a rotated window) runs zero key chunks: no exponentials, no P rows (its O rows are
+            // never stored) — only the barrier protocol
+            const int nch = (skip_empty && (q0 + warp * 32 >= L || q0 + warp * 32 + 32 <= lo)) ? 0 : (L + 31) >> 5;
             if (((L + 15) & ~15) > ATC_LONG)  // the MMA warp waits for these before it may issue S(it)
                 while (pend < it) readout(pend++);
             ptx::mbar_wait(s_ready, it & 1);
@@ -312,7 +329,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
             const float inv = 1.0f / sum;
-            const long long off = q < L ? static_cast<long long>(cur.x + q) * hidden + h * ATC_HD : -1;
+            const long long off = (q >= lo && q < L) ? static_cast<long long>(cur.x + q) * hidden + h * ATC_HD : -1;
             if (it & 1) { inv_sum[1] = inv; out_off[1] = off; } else { inv_sum[0] = inv; out_off[0] = off; }
             while (pend < it) readout(pend++);  // O(it - 1): its P.V was issued long ago; runs while P.V(it) and S(it + 1) execute
             cur = nxt;
@@ -373,10 +390,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             const int w = blockIdx.x + it * gridDim.x;
             const int4 nxt = it + 1 < n_it ? __ldg(&desc[(w + gridDim.x) / heads]) : cur;
             const int h = w % heads;
-            const int qb = cur.z;
+            const int q0 = cur.z & 0xffff, lo = cur.z >> 16;
             const int L = cur.y;
-            const int q = qb * ATC_TM + row;
-            const int nch = (skip_empty && qb * ATC_TM + q4 * 32 >= L) ? 0 : (L + 31) >> 5;
+            const int q = q0 + row;
+            const int nch = (skip_empty && (q0 + q4 * 32 >= L || q0 + q4 * 32 + 32 <= lo)) ? 0 : (L + 31) >> 5;
             const int xb = (it & 1) * 2;
             if (((L + 15) & ~15) > ATC_LONG) {  // the MMA warp waits for these before it may issue S(it)
                 pair_sync();                   // the partner's partial sums of item it - 1 are in shared memory
@@ -439,7 +456,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
-            const long long off = q < L ? static_cast<long long>(cur.x + q) * hidden + h * ATC_HD : -1;
+            const long long off = (q >= lo && q < L) ? static_cast<long long>(cur.x + q) * hidden + h * ATC_HD : -1;
             if (it & 1) out_off[1] = off; else out_off[0] = off;
             while (pend < it) readout(pend++);
             cur = nxt;
@@ -468,7 +485,10 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
     int4* desc = reinterpret_cast<int4*>(items);  // 2 descriptors per passage at most: fits the [n_seq * 8] int work-list buffer
     if (build_items) {  // once per encoder pass: the list is the same for every layer
         LB2_CUDA_OK(cudaMemsetAsync(item_count, 0, sizeof(int), s));
-        attention_tc_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_start, seq_len, n_seq, row_base, desc, item_count);
+        // LB2_ATTN_ROTATE = 0: every second-block tail in row quarter 0 (the layout before the rotation; A/B switch)
+        const char* rt = getenv("LB2_ATTN_ROTATE");
+        attention_tc_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_start, seq_len, n_seq, row_base, desc, item_count,
+                                                                      rt ? atoi(rt) : 1);
         LB2_CUDA_OK(cudaGetLastError());
     }
     CUtensorMap tm_qk, tm_v;

@@ -172,6 +172,39 @@ def test_attention_tc_8_softmax_warps_matches_4(lib, cuda_ok, monkeypatch):
     assert (out[0] - out[1]).abs().max().item() <= 2e-3
 
 
+def test_attention_tc_rotated_tail_blocks(lib, cuda_ok, monkeypatch):
+    """Second query blocks (rows 128 .. L-1) are placed in a row quarter drawn per passage (attention_tc_items_kernel: the
+    A descriptor of S starts rot * 32 rows earlier, the warps below the tail idle).  Every tail length 1 .. 128 several times,
+    so that each rotation of each table entry occurs: against torch, and bit-identical to the unrotated layout
+    (LB2_ATTN_ROTATE=0) — a row's arithmetic does not depend on the TMEM lane it runs in."""
+    H, heads, hd = 384, 12, 32
+    lens = [L for L in range(129, 257)] * 3 + [1, 16, 100, 128, 31, 64]
+    T = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = (torch.randn(T, 3 * H, device="cuda", generator=g) * 1.5).half()
+    dl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    ds = (torch.cumsum(dl, 0) - dl).to(torch.int32)
+    qkvh = qkv.view(T, 3, heads, hd).permute(2, 0, 1, 3).contiguous()
+    out = {}
+    for rot in ("1", "0"):
+        monkeypatch.setenv("LB2_ATTN_ROTATE", rot)
+        ctx = torch.full((T, H), float("nan"), device="cuda", dtype=torch.float16)
+        assert lib.lb2_test_attention_f16(qkvh.data_ptr(), ds.data_ptr(), dl.data_ptr(), len(lens), T, H, heads, 256, ctx.data_ptr()) == 0, lib.lb2_last_error()
+        torch.cuda.synchronize()
+        out[rot] = ctx
+    assert torch.isfinite(out["1"]).all() and torch.isfinite(out["0"]).all()
+    assert torch.equal(out["1"], out["0"])
+    off, worst = 0, 0.0
+    for L in lens:
+        blk = qkv[off:off + L].float()
+        q, k, v = (blk[:, i * H:(i + 1) * H].reshape(L, heads, hd).transpose(0, 1) for i in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / hd ** 0.5, dim=-1)
+        ref = (p @ v).transpose(0, 1).reshape(L, H)
+        worst = max(worst, (out["1"][off:off + L].float() - ref).abs().max().item())
+        off += L
+    assert worst <= 4e-3, worst
+
+
 @pytest.mark.parametrize("M", [129, 5000])
 @pytest.mark.parametrize("epi", [0, 1])
 def test_gemm_weight_stationary_direct_store_matches_tma_store(lib, cuda_ok, M, epi, monkeypatch):
