@@ -60,13 +60,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // work list: one descriptor per (passage, 128-row query block): {first packed row of the passage, length, query window, passage}.
 // One 16-byte load per work item in the kernel (no dependent items -> seq_len -> seq_start chain); a passage's blocks are adjacent.
 // query window z = q0 | lo << 16: the item's 128 MMA rows are the passage's rows [q0, q0 + 128); rows in [lo, L) are its
-// output.  First block: q0 = lo = 0.  Second block (rows 128 .. L-1, usually only one or two warps' worth): its rows may sit
-// in ANY row quarter of the tile — q0 = 128 - 32 * rot puts them rot quarters up (the A operand is the same (q | k) tile,
-// only the descriptor start moves by rot * 4 KB; the rows below lo are first-block rows whose warps idle).  Softmax warp w
-// lives on SM sub-partition w, and the exponentials of a sub-partition are the bound of this kernel: with every tail in
-// quarter 0, sub-partition 0 carried 1.31x the mean MUFU load on the bench corpus' length mix (N(128, 48)) and sub-partition
-// 3 0.72x.  The rotation is drawn per passage from small tables weighted towards the upper quarters (short first blocks load
-// the lower ones): max / mean = 1.01 on that mix (scripts in DESIGN.md §3).
+// output.  First block: q0 = lo = 0.  Second block (rows 128 .. L-1, usually only one or two warps' worth): q0 = lo = 128,
+// or — LB2_ATTN_ROTATE=1, an experiment kept as a switch — q0 = 128 - 32 * rot, which puts the tail rot row quarters up
+// (the A operand is the same (q | k) tile, only the descriptor start moves by rot * 4 KB; the warps below lo idle).
+// Why: softmax warp w lives on SM sub-partition w, and with every tail in quarter 0 sub-partition 0 carries 1.31x the mean
+// MUFU load on the bench corpus' length mix (N(128, 48)), sub-partition 3 0.72x; the tables below bring max / mean to 1.01
+// (scripts/attn_rotation_model.py).  Measured (profiles/r02e_attention_rotation_ab.log): bit-identical outputs and NO
+// change in time (0.786 vs 0.788 ms) — the kernel is bound by the per-item chain S -> softmax -> P.V of a CTA (a tail item
+// costs a full item whatever its warps do), not by MUFU throughput per sub-partition.  Default off.
 __constant__ uint8_t ATC_ROT1[8] = {3, 3, 3, 3, 3, 3, 0, 1};  // tail of <= 32 rows
 __constant__ uint8_t ATC_ROT2[8] = {2, 2, 2, 2, 2, 0, 0, 0};  // tail of <= 64 rows (<= 96 and more: no rotation)
 __global__ void attention_tc_items_kernel(const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len, int n_seq,
@@ -485,10 +486,10 @@ bool launch_attention_tc(cudaStream_t s, const __half* qkv, const int32_t* seq_s
     int4* desc = reinterpret_cast<int4*>(items);  // 2 descriptors per passage at most: fits the [n_seq * 8] int work-list buffer
     if (build_items) {  // once per encoder pass: the list is the same for every layer
         LB2_CUDA_OK(cudaMemsetAsync(item_count, 0, sizeof(int), s));
-        // LB2_ATTN_ROTATE = 0: every second-block tail in row quarter 0 (the layout before the rotation; A/B switch)
+        // LB2_ATTN_ROTATE = 1: second-block tails in a row quarter drawn per passage (A/B switch; measured neutral, default 0)
         const char* rt = getenv("LB2_ATTN_ROTATE");
         attention_tc_items_kernel<<<(n_seq + 255) / 256, 256, 0, s>>>(seq_start, seq_len, n_seq, row_base, desc, item_count,
-                                                                      rt ? atoi(rt) : 1);
+                                                                      rt ? atoi(rt) : 0);
         LB2_CUDA_OK(cudaGetLastError());
     }
     CUtensorMap tm_qk, tm_v;
