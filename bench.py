@@ -237,6 +237,28 @@ def ensure_world(args, builder: bool, device: int) -> Path:
     return wd
 
 
+def library_rendezvous(build, rank: int, world: int, cache: str, timeout_s: float = 900.0):
+    """Rank 0 (re)builds libleann_b200.so when its sources are newer; under torchrun the other ranks must not dlopen a
+    half-linked file, so they wait for a marker that rank 0 writes once the library is in place (one marker per launch:
+    the ranks of a launch share MASTER_PORT and their parent, the elastic agent)."""
+    if world == 1:
+        if build.needs_build():
+            build.build()
+        return
+    marker = Path(cache) / f".lib_ready_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+    if rank == 0:
+        if build.needs_build():
+            build.build()
+        marker.parent.mkdir(parents=True, exist_ok=True)
+        marker.write_text(str(time.time()))
+    else:
+        t0 = time.time()
+        while not marker.exists():
+            if time.time() - t0 > timeout_s:
+                raise RuntimeError(f"timed out waiting for rank 0 to provide the library ({marker})")
+            time.sleep(0.2)
+
+
 def load_world(wd: Path):
     from leann_b200 import synth
 
@@ -271,8 +293,7 @@ def run_b200(args):
     from leann_b200 import backend, build
     from leann_b200.tooling import recall_at_k
 
-    if build.needs_build() and rank == 0:
-        build.build()
+    library_rendezvous(build, rank, world, args.cache)
     wd = ensure_world(args, builder=(rank == 0), device=local)  # file-system rendezvous BEFORE the process group exists
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

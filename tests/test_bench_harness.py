@@ -91,3 +91,35 @@ def test_ranks_wait_for_the_builders_done_marker(bench, tmp_path, monkeypatch):
     args.rebuild = True
     bench.ensure_world(args, builder=True, device=0)
     assert built == [0, 0]
+
+
+def test_other_ranks_wait_until_rank0_has_the_library_in_place(bench, tmp_path, monkeypatch):
+    """library_rendezvous: with sources newer than the .so, rank 0 rebuilds; ranks > 0 neither build nor return before it is done."""
+    monkeypatch.setenv("MASTER_PORT", "29999")
+    events = []
+
+    class FakeBuild:
+        @staticmethod
+        def needs_build():
+            return True
+
+        @staticmethod
+        def build():
+            events.append("build-start")
+            time.sleep(0.6)
+            events.append("build-end")
+
+    def other():
+        bench.library_rendezvous(FakeBuild, 1, 2, str(tmp_path), timeout_s=10)
+        events.append("rank1-go")
+
+    t = threading.Thread(target=other)
+    t.start()
+    time.sleep(0.1)
+    bench.library_rendezvous(FakeBuild, 0, 2, str(tmp_path))
+    t.join(10)
+    assert events == ["build-start", "build-end", "rank1-go"]
+    # a lone process just builds
+    events.clear()
+    bench.library_rendezvous(FakeBuild, 0, 1, str(tmp_path))
+    assert events == ["build-start", "build-end"]
