@@ -53,6 +53,37 @@ def test_oracle_vs_compiled_reference_random(metric_ip):
             assert np.array_equal(u, v)
 
 
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built (only possible in the dev container)")
+@pytest.mark.parametrize("seed", range(10))
+def test_oracle_vs_compiled_reference_fuzz(seed):
+    """Randomised shapes and search parameters, on purpose degenerate: integer-valued coordinates (many exactly equal
+    distances -> every tie-break of the heaps, the beam and the result handler matters), duplicate vectors, k above and below
+    efSearch, more results requested than nodes reachable, beam / batch modes, both metrics, the relative-distance stop rule on
+    and off.  The C restatement must return the compiled reference's ids, distances, ndis and nhops exactly."""
+    from oracle.binding import export_to_csr
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([12, 60, 400, 1500]))
+    d = int(rng.choice([4, 16, 33]))
+    M = int(rng.choice([4, 8, 16]))
+    metric_ip = bool(rng.integers(0, 2))
+    x = rng.integers(-3, 4, (n, d)).astype(np.float32)
+    x[rng.integers(0, n, n // 10 + 1)] = x[0]                      # exact duplicates of one vector
+    q = np.concatenate([rng.integers(-3, 4, (12, d)), x[:4]]).astype(np.float32)   # some queries ARE data points
+    R = Reference(d, M=M, metric_ip=metric_ip)
+    R.build(x, ef_construction=int(rng.choice([16, 40])), nthreads=1)
+    O = Oracle(export_to_csr(R.export()), x)
+    for _ in range(5):
+        ef = int(rng.choice([1, 3, 10, 32, 64]))
+        beam = int(rng.choice([1, 1, 2, 5]))
+        batch = int(rng.choice([0, 0, 7, 40]))
+        cr = bool(rng.integers(0, 2))
+        k = int(rng.choice([1, 5, 10, 40]))
+        a = R.search(q, k, ef=ef, beam=beam, batch_size=batch, check_rel=cr)
+        b = O.search(q, k, ef=ef, beam=beam, batch_size=batch, check_rel=cr)
+        for name, u, v in zip(("D", "I", "ndis", "nhops"), a, b):
+            assert np.array_equal(u, v), (name, dict(n=n, d=d, M=M, ip=metric_ip, ef=ef, beam=beam, batch=batch, cr=cr, k=k))
+
+
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
 def test_minimax_heap_vs_reference():
     """Random push / pop_min / count_below traces incl. equal and infinite distances
