@@ -9,8 +9,9 @@ faiss/impl/HNSW.cpp:600-894), applied as whole-graph sweeps.  `search_fn` is any
 stored-vector search (capi.Index.search(..., recompute=False), 6e5 queries/s, i.e. tens of seconds per sweep at 10 M) in
 production, the CPU oracle in the unit test.
 
-Status: validated on CPU at small scale (tests/test_graph_refine.py); not yet wired into bench.py — the large-scale run needs
-GPU time that round 1 no longer had.
+Status: validated on CPU at small scale (tests/test_graph_refine.py); bench.py exposes the sweeps as --sweeps (default 0: the
+insertion-as-search builder of graph_build.py reaches the target recall without them).  `prune_degrees` (below) is the
+reference's per-node degree cap for the pruned-degree configuration.
 """
 from __future__ import annotations
 
@@ -141,3 +142,58 @@ def gpu_searcher(vectors_device_ptr: int, workdir, ef: int = 128, k: int = 48, d
         return search
 
     return make
+
+
+@torch.no_grad()
+def prune_degrees(x, g: CSRGraph, M: int = 32, hub_fraction: float = 0.02, low: tuple[int, int] = (6, 7), seed: int = 789,
+                  by: str = "in", device: str | None = None) -> tuple[CSRGraph, np.ndarray]:
+    """High-degree-preserving pruning of the level-0 adjacency — the per-node degree cap `ems` of the reference's builder
+    (faiss/IndexHNSW.cpp:130-225, hnsw.ems; consumed at faiss/impl/HNSW.cpp:762-763 where the new node's candidate list is
+    shrunk to ems[pt_id] instead of M0).  The reference ships that branch switched off (`bool prune = false`), with the
+    policy written out beside it: nodes whose degree is in the top 2 % keep M0 = 2M links, every other node keeps 6 or 7
+    (`6 + rng.rand_int(2)`), chosen from its links by the usual neighbour-selection heuristic (shrink_neighbor_list).  This
+    is that policy applied to a finished graph, as BASELINE.json's pruned-degree configuration (C5) needs:
+
+      hubs  = the `hub_fraction` of nodes with the largest degree (`by` = "in": number of level-0 lists a node appears in —
+              what makes a node a hub for the traversal; "out": length of its own list, which is what a degree file written
+              from a stored graph holds)
+      ems_i = 2M for hubs, low[0] + (0 or 1) for the others
+      list_i <- neighbour-selection heuristic over list_i (ascending distance), at most ems_i kept, no fill
+
+    Upper levels, levels and the entry point are untouched (the reference sets ems = infinity above level 0).  Returns the
+    new graph and ems [n]."""
+    if by not in ("in", "out"):
+        raise ValueError("by must be 'in' or 'out'")
+    metric_ip = g.metric_type == METRIC_INNER_PRODUCT
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    xt = xt.to(dev, torch.float32)
+    n = g.ntotal
+    l0 = level0_padded(g, 2 * M)
+    deg_out = (l0 >= 0).sum(1)
+    degree = np.bincount(l0[l0 >= 0], minlength=n) if by == "in" else deg_out
+    n_hub = max(1, int(n * hub_fraction))
+    threshold = np.sort(degree)[::-1][n_hub - 1]
+    hub = degree >= threshold
+    rng = np.random.default_rng(seed)
+    ems = np.where(hub, 2 * M, low[0] + rng.integers(0, low[1] - low[0] + 1, n)).astype(np.int32)
+    # candidates of every node = its own list in ascending distance
+    ci = torch.from_numpy(l0).to(dev)
+    cd = torch.full(ci.shape, float("inf"), dtype=torch.float32, device=dev)
+    sq = (xt * xt).sum(1)
+    for b0 in range(0, n, 1 << 16):
+        b1 = min(n, b0 + (1 << 16))
+        cc = ci[b0:b1].clamp(min=0)
+        ip = torch.bmm(xt[cc], xt[b0:b1].unsqueeze(2)).squeeze(2)
+        d = -ip if metric_ip else (sq[b0:b1, None] + sq[cc] - 2 * ip)
+        cd[b0:b1] = torch.where(ci[b0:b1] >= 0, d, cd[b0:b1])
+    o = torch.argsort(cd, dim=1, stable=True)
+    ci, cd = torch.gather(ci, 1, o), torch.gather(cd, 1, o)
+    kept = _heuristic_prune(xt, ci, cd, low[1], metric_ip, fill=False).cpu().numpy()   # [n, low[1]], selection order
+    col = np.arange(kept.shape[1])[None, :]
+    kept[col >= ems[:, None]] = -1                                                       # the nodes drawn with the smaller cap
+    new0 = np.full_like(l0, -1)
+    new0[:, : kept.shape[1]] = kept
+    new0[hub] = l0[hub]
+    g2 = csr_from_padded(g.d, g.metric_type, g.levels, new0.astype(np.int32), upper_levels(g, M), g.entry_point, M=M)
+    return g2, ems

@@ -57,3 +57,53 @@ def test_partition_restricted_lists_work_on_tiny_member_sets():
     q = x[:50]
     _, I, _, _ = Oracle(g, x).search(q, 1, ef=32)
     assert (I[:, 0] == np.arange(50)).mean() > 0.9   # navigable: a point finds itself
+
+
+def test_high_degree_preserving_pruning_keeps_hubs_and_caps_the_rest(tmp_path):
+    """graph_refine.prune_degrees = the `ems` policy written in the reference's builder (faiss/IndexHNSW.cpp:130-225: top 2 % by
+    degree keep M0, the rest 6 or 7 links chosen by the neighbour-selection heuristic), applied to a finished graph."""
+    from leann_b200 import csr
+    from leann_b200.graph_refine import prune_degrees
+
+    rng = np.random.default_rng(3)
+    n, d, M = 8000, 32, 16
+    cen = rng.standard_normal((n // 40, d)).astype(np.float32)
+    x = cen[rng.integers(0, len(cen), n)] + 0.5 * rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = x[rng.integers(0, n, 200)] + 0.05 * rng.standard_normal((200, d)).astype(np.float32)
+    gt = np.argsort(-(q @ x.T), axis=1)[:, :10]
+
+    def recall(g, ef):
+        _, I, _, _ = Oracle(g, x).search(q.astype(np.float32), 10, ef=ef, nthreads=8)
+        return float(np.mean([len(set(I[i]) & set(gt[i])) / 10 for i in range(len(q))]))
+
+    g = gb.build_hnsw_graph(x, M=M, metric="mips", device="cpu")
+    g2, ems = prune_degrees(x, g, M=M, device="cpu")
+    a, b = level0_padded(g, 2 * M), level0_padded(g2, 2 * M)
+    deg_in = np.bincount(a[a >= 0], minlength=n)
+    hub = ems == 2 * M
+    # the hubs are the top 2 % by in-degree (ties at the threshold included) and keep their lists verbatim
+    assert int(n * 0.02) <= hub.sum() <= int(n * 0.03) and deg_in[hub].min() >= deg_in[~hub].max()
+    assert np.array_equal(a[hub], b[hub])
+    # everybody else: at most ems links, all of them taken from the old list, no self loops, never emptied
+    deg2 = (b >= 0).sum(1)
+    assert set(np.unique(ems[~hub])) == {6, 7} and (deg2[~hub] <= ems[~hub]).all() and (deg2 >= 1).all()
+    for i in rng.integers(0, n, 300):
+        assert set(b[i][b[i] >= 0]) <= set(a[i][a[i] >= 0])
+    assert not (b == np.arange(n)[:, None]).any()
+    # what it is for: far fewer edges to store and to follow ...
+    assert g2.neighbors.size < 0.65 * g.neighbors.size   # mean degree 13.4 -> 7.6 here; 24 -> 7 on the bench graph (M = 32)
+    # ... upper levels, levels and entry point untouched, file format unchanged
+    assert np.array_equal(g.levels, g2.levels) and g.entry_point == g2.entry_point
+    up_a, up_b = upper_levels(g, M), upper_levels(g2, M)
+    assert up_a.keys() == up_b.keys() and all(np.array_equal(up_a[l][1], up_b[l][1]) for l in up_a)
+    f = tmp_path / "pruned.index"
+    csr.write_compact_index(str(f), g2)
+    g3 = csr.read_compact_index(str(f))
+    assert np.array_equal(g3.neighbors, g2.neighbors) and np.array_equal(g3.level_ptr, g2.level_ptr)
+    # ... and the accuracy is bought back with a wider beam (the ef sweep of the pruned-graph configuration)
+    r_full, r_64, r_256 = recall(g, 64), recall(g2, 64), recall(g2, 256)
+    assert r_full > 0.9 and r_256 > r_64 and r_256 >= r_full - 0.1, (r_full, r_64, r_256)
+    # out-degree flavour: hubs by the length of their own list
+    _, ems_out = prune_degrees(x, g, M=M, by="out", device="cpu")
+    assert (ems_out == 2 * M).sum() >= int(n * 0.02)
