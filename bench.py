@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--efc", type=int, default=int(os.environ.get("LB2_BENCH_EFC", 200)), help="efConstruction of the graph build")
     ap.add_argument("--sweeps", type=int, default=int(os.environ.get("LB2_BENCH_SWEEPS", 0)), help="graph build: repair sweeps")
+    ap.add_argument("--ems", action="store_true", help="degree-pruned graph (configs[4] variant): top 2 %% of nodes by in-degree keep "
+                    "2M level-0 links, the others 6-7 (graph_refine.prune_degrees = the reference's ems policy); not the headline")
     ap.add_argument("--pool", type=int, default=65536, help="size of the query pool (with exact ground truth)")
     ap.add_argument("--slots", type=int, default=int(os.environ.get("LB2_SLOTS", 1024)))
     ap.add_argument("--per-pass", type=int, default=int(os.environ.get("LB2_PER_PASS", 0)))
@@ -114,8 +116,11 @@ class ClockSampler:
 def world_dir(args) -> Path:
     from leann_b200 import synth
 
-    key = json.dumps({"v": WORLD_VERSION, "chunks": args.chunks, "model": synth.MINILM_L6.name, "M": 32, "efc": args.efc,
-                      "sweeps": args.sweeps, "pool": args.pool}, sort_keys=True)
+    cfg = {"v": WORLD_VERSION, "chunks": args.chunks, "model": synth.MINILM_L6.name, "M": 32, "efc": args.efc,
+           "sweeps": args.sweeps, "pool": args.pool}
+    if getattr(args, "ems", False):
+        cfg["ems"] = "top2pct_in_degree_keep_2M_else_6_7"
+    key = json.dumps(cfg, sort_keys=True)
     return Path(args.cache) / f"c{args.chunks}_{hashlib.sha1(key.encode()).hexdigest()[:12]}"
 
 
@@ -200,6 +205,11 @@ def build_world(args, wd: Path, device: int):
     else:
         g = build_hnsw_graph(E, M=32, metric="mips", device=f"cuda:{device}")
         info["graph_builder"] = "exact batch builder (small corpus)"
+    if getattr(args, "ems", False):
+        from leann_b200.graph_refine import prune_degrees
+        full_edges = int(g.neighbors.size)
+        g, _ = prune_degrees(E, g, M=32, device=f"cuda:{device}")
+        info["graph_builder"] += f" + high-degree-preserving pruning (top 2 % keep 64 links, others 6-7; {full_edges} -> {int(g.neighbors.size)} edges)"
     torch.cuda.synchronize()
     info.update(graph_s=time.time() - t2, edges=int(g.neighbors.size), max_level=int(g.max_level))
     log(f"graph: {g.neighbors.size/1e6:.1f} M edges, max_level {g.max_level} ({info['graph_s']:.1f}s)")
